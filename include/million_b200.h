@@ -1,0 +1,189 @@
+/* million_b200.h — C ABI of libmillion_b200.so: the B200-native (sm_100a) implementation of
+ * MILLION's product-quantized KV-cache hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one native/third-party call of the
+ * reference (paths relative to the reference checkout, Zhaohui-Xu/MILLION):
+ *
+ *   million_pq_encode            scripts/utils/pq_utils.py:451-499  sa_encode_4d_keops (pykeops arg-min),
+ *                                call sites pq_utils.py:235-236, 292-293; paged_pq_utils.py:161-167, 241-242
+ *   million_pq_encode_paged      + the page write of scripts/utils/dynamic_paged_pq_utils.py:768-811
+ *   million_pq_decode            scripts/utils/pq_utils.py:501-540  sa_decode_4d (torch.gather)
+ *   million_pq_decode_attn       scripts/modeldb/bindings/Interface.cu:16-120
+ *                                flash_decoding_allocated_buffer<...> (at::matmul LUT + split + residual +
+ *                                reduce kernels, bindings/Kernel.cuh:11-166, 1038-1209, 1211-1270), bound
+ *                                to Python at bindings/bindings.template.cpp:50-62; and the paged variant
+ *                                the live cache asks for at scripts/utils/paged_pq_utils.py:547, 621-635
+ *   million_lse_merge            scripts/modeldb/bindings/Kernel.cuh:1211-1270 flash_decoding_reduce_kernel
+ *                                (used here for the cross-GPU split-KV merge; the reference has no multi-GPU)
+ *   million_window_append        scripts/utils/pq_utils.py:304-311 (copy of the new k/v into the fp16 window)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA device unless
+ *     its name ends in _host; no torch types; no exceptions cross this boundary.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *     The reference launches on the legacy default stream (Interface.cu:65,88,109); callers here pass the
+ *     current torch stream.
+ *   - return value: MILLION_OK or a million_status; the reference printed and exit()ed on a launch error
+ *     (Interface.cu:3-11), we return the code and keep a thread-local message (million_last_error()).
+ *   - inputs are borrowed, outputs/scratch are caller-owned.  Nothing is allocated by the library except
+ *     small per-device constants on first use.
+ *   - there is no CPU fallback: without a CUDA device every compute call returns MILLION_ERR_CUDA.
+ */
+#ifndef MILLION_B200_H_
+#define MILLION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MILLION_ABI_VERSION 1
+
+typedef void* million_stream_t; /* cudaStream_t */
+
+enum million_dtype { MILLION_F16 = 0, MILLION_BF16 = 1, MILLION_F32 = 2 };
+
+enum million_status {
+    MILLION_OK = 0,
+    MILLION_ERR_INVALID = 1,     /* bad argument (null pointer, inconsistent sizes) */
+    MILLION_ERR_UNSUPPORTED = 2, /* shape/dtype combination not compiled */
+    MILLION_ERR_CUDA = 3         /* CUDA runtime error; see million_last_error() */
+};
+
+/* value_codes layouts understood by million_pq_decode_attn / written by the encoders */
+enum million_v_layout {
+    MILLION_V_ROWMAJOR = 0,   /* (bs, nh_k, nk, M)           pq_utils.py:117-125 */
+    MILLION_V_TRANSPOSED = 1, /* (bs, nh_k, M, ld>=nk)       paged_pq_utils.py:77-80 (live PagedPQCache) */
+    MILLION_V_PAGED = 2       /* pool (pages, M, page_size) + block table (bs, nh_k, n_pages) int64
+                                 dynamic_paged_pq_utils.py:46-48, 453-456; paged_pq_utils.py:621-635 */
+};
+
+/* which implementation to run; AUTO picks the fastest one that supports the shape */
+enum million_impl {
+    MILLION_IMPL_AUTO = 0,
+    MILLION_IMPL_GENERIC = 1, /* plain SIMT kernels, every shape */
+    MILLION_IMPL_FAST = 2     /* decode: shared-memory LUT + mma reduction; encode: tcgen05 distances */
+};
+
+int million_abi_version(void);
+const char* million_last_error(void);
+/* sm_count / cc of the current device; MILLION_ERR_CUDA when there is none */
+int million_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder: codes[v, m] = argmin_c sum_k (fp32(x[v, m*d_m + k]) - cent[m, c, k])^2, first minimum wins.
+ * Replaces sa_encode_4d_keops (pq_utils.py:451-499).
+ *
+ *   x         n_heads blocks of n_tokens rows of d values (x_dtype), block stride x_head_stride ELEMENTS
+ *             (so a slice [:, :, :64, :] of a (bs, nh_k, Lt, d) window can be encoded in place)
+ *   cent      (M, C, d/M) fp32, contiguous (the reference casts to fp32 too, pq_utils.py:484)
+ *   codes     element (head, t, m) is written at
+ *                 codes + head*codes_head_stride + (t0 + t)*codes_token_stride + m*codes_m_stride   (ELEMENTS)
+ *             row-major cache (bs,nh_k,cap,M): token_stride=M, m_stride=1; transposed (bs,nh_k,M,cap):
+ *             token_stride=1, m_stride=cap.  code_bytes = 1 (C<=256) or 2 (C<=65536, nbits2dtype).
+ */
+int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride,
+                      const float* cent,
+                      void* codes, int code_bytes,
+                      int64_t codes_head_stride, int64_t codes_token_stride, int64_t codes_m_stride,
+                      int64_t t0,
+                      int n_heads, int n_tokens, int d, int M, int C,
+                      int impl, million_stream_t stream);
+
+/* Same arg-min, written into a page pool (pages, M, page_size) uint8 through a block table:
+ * token (t0+t) of head `head` goes to pool[page_ids[head*page_ids_head_stride + (t0+t)/page_size], m, (t0+t)%page_size].
+ * Format: dynamic_paged_pq_utils.py:46-48, 768-811. */
+int million_pq_encode_paged(const void* x, int x_dtype, int64_t x_head_stride,
+                            const float* cent,
+                            uint8_t* page_pool, const int64_t* page_ids, int64_t page_ids_head_stride,
+                            int page_size, int64_t t0,
+                            int n_heads, int n_tokens, int d, int M, int C,
+                            int impl, million_stream_t stream);
+
+/* Reconstruct: out[v, m*d_m + k] = cent[m, codes[v, m], k].  Replaces sa_decode_4d (pq_utils.py:501-540).
+ * cent/out share `dtype` (the reference returns C's dtype).  codes addressed like in million_pq_encode. */
+int million_pq_decode(const void* codes, int code_bytes,
+                      int64_t codes_head_stride, int64_t codes_token_stride, int64_t codes_m_stride,
+                      const void* cent, void* out, int dtype, int64_t out_head_stride,
+                      int n_heads, int n_tokens, int d, int M, int C,
+                      million_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode attention of ONE new query token per (batch, head) over nk PQ-coded tokens plus the r most
+ * recent tokens kept in fp16/bf16 ("residual window"), no mask:
+ *     s_j = scale * sum_m <q_h[m], Kcent[m, Kcode[b,hk,j,m]]>   (j <  nk)   hk = h / (nh/nh_k)
+ *     s_j = scale * <q_h, Kres[b,hk,j-nk]>                       (j >= nk)
+ *     o_h = softmax(s) . [decode(Vcode) ; Vres]
+ * One launch does what Interface.cu:16-120 does with one cuBLAS call + three kernels.
+ */
+typedef struct million_attn_params {
+    uint32_t struct_size; /* = sizeof(million_attn_params) */
+    int32_t io_dtype;     /* MILLION_F16 | MILLION_BF16: dtype of q, cents, residuals, out */
+    int32_t impl;         /* million_impl */
+    int32_t flags;        /* MILLION_ATTN_* */
+
+    int32_t bs, nh, nh_k, d, M, C;
+    int32_t nk; /* quantized tokens per head, >= 0 */
+    int32_t r;  /* valid residual rows, 0 <= r <= res_len (the reference requires r > 0) */
+
+    const void* q; /* (bs, nh, d) — the reference's (bs, nh, 1, d) */
+    const uint8_t* k_codes; /* (bs, nh_k, nk, M) row-major */
+    int64_t k_head_stride;  /* BYTES between consecutive (b, hk) blocks (>= nk*M; lets a preallocated cache be used) */
+
+    int32_t v_layout;       /* million_v_layout */
+    int32_t page_size;      /* V_PAGED */
+    const uint8_t* v_codes; /* ROWMAJOR/TRANSPOSED: first byte of head (0,0); PAGED: the page pool */
+    int64_t v_head_stride;  /* BYTES between (b, hk) blocks (unused for PAGED) */
+    int64_t v_ld;           /* TRANSPOSED: bytes between consecutive m rows */
+    const int64_t* v_page_ids; /* PAGED: (bs, nh_k, n_pages) */
+    int32_t n_pages;
+    int32_t res_len; /* rows allocated per head in k_res/v_res (Lt) */
+
+    const void* k_cent; /* (M, C, d/M) io_dtype */
+    const void* v_cent;
+    const void* k_res; /* (bs, nh_k, res_len, d) io_dtype; rows [0, r) valid */
+    const void* v_res;
+
+    void* out; /* (bs, nh, d) io_dtype; NULL allowed with MILLION_ATTN_PARTIAL_ONLY */
+
+    /* scratch, caller-owned: million_pq_decode_attn_workspace_bytes(...) bytes, 16-byte aligned.  The first
+     * 4*bs*nh_k bytes are arrival counters that must be zero before the FIRST call; the kernel leaves them
+     * zero again. */
+    void* workspace;
+    int64_t workspace_bytes;
+    int32_t n_splits; /* CTAs per (b, kv-head) over the token range; 0 = choose from the SM count */
+
+    /* split-KV across GPUs: with MILLION_ATTN_PARTIAL_ONLY the merged but UN-normalised state of this rank
+     * is written here as fp32 (bs, nh, d+2) = [o_unnormalised (d) | running max m | denominator l] and `out`
+     * is not touched.  Merge ranks with million_lse_merge. */
+    float* partial;
+} million_attn_params;
+
+#define MILLION_ATTN_PARTIAL_ONLY 1
+
+int64_t million_pq_decode_attn_workspace_bytes(int bs, int nh, int nh_k, int d, int max_splits);
+/* the split count AUTO would use (so callers can size the workspace) */
+int million_pq_decode_attn_default_splits(int bs, int nh_k, int nk);
+int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream);
+
+/* Merge n_parts partial states (n_parts, bs*nh, d+2) fp32 [o_unnorm | m | l] -> out (bs*nh, d) io_dtype.
+ * Same algebra as flash_decoding_reduce_kernel (Kernel.cuh:1249-1269); empty parts (l = 0) are skipped. */
+int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype,
+                      million_stream_t stream);
+
+/* window[(head), r0 + i, :] = src[(head), i, :] for i < n — pq_utils.py:304-311, paged_pq_utils.py:377-378.
+ * Both K and V in one launch.  Strides in ELEMENTS. */
+int million_window_append(void* k_win, void* v_win, int64_t win_head_stride,
+                          const void* k_src, const void* v_src, int64_t src_head_stride,
+                          int n_heads, int r0, int n, int d, int dtype, million_stream_t stream);
+
+/* window[:, 0:rem, :] = window[:, shift:shift+rem, :] (paged flush, paged_pq_utils.py:186-199) */
+int million_window_shift(void* k_win, void* v_win, int64_t win_head_stride, int n_heads, int shift, int rem,
+                         int d, int dtype, million_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MILLION_B200_H_ */

@@ -1,0 +1,203 @@
+// c_api.cu — extern "C" entry points of libmillion_b200.so (include/million_b200.h): argument checks,
+// implementation choice, launches.  No torch, no exceptions, no host synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "attn_common.cuh"
+
+namespace million {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return MILLION_ERR_CUDA;
+}
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+struct CodeDst;
+int launch_attn_generic(const AttnArgs& a, int io_dtype, cudaStream_t stream);
+int launch_attn_fast(const AttnArgs& a, int io_dtype, cudaStream_t stream, bool probe_only);
+int launch_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, cudaStream_t stream);
+int launch_reconstruct(const void* codes, int code_bytes, int64_t chs, int64_t cts, int64_t cms, const void* cent, void* out,
+                       int dtype, int64_t ohs, int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream);
+int launch_rows_copy2(void* k_dst, void* v_dst, int64_t dst_hs_b, int64_t dst_off_b, const void* k_src, const void* v_src,
+                      int64_t src_hs_b, int64_t src_off_b, int n_heads, int64_t bytes_per_head, cudaStream_t stream);
+int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float* cent, void* codes, int code_bytes, int64_t chs,
+                    int64_t cts, int64_t cms, int64_t t0, const int64_t* page_ids, int64_t pihs, int page_size, int n_heads,
+                    int n_tokens, int d, int M, int C, int impl, cudaStream_t stream);
+
+static inline int elem_bytes(int dtype) { return dtype == MILLION_F32 ? 4 : 2; }
+
+}  // namespace million
+
+using namespace million;
+
+extern "C" {
+
+int million_abi_version(void) { return MILLION_ABI_VERSION; }
+const char* million_last_error(void) { return g_err; }
+
+int million_device_info(int* sms, int* major, int* minor) {
+    int dev = 0;
+    MILLION_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    MILLION_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    if (sms) *sms = p.multiProcessorCount;
+    if (major) *major = p.major;
+    if (minor) *minor = p.minor;
+    return MILLION_OK;
+}
+
+int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, void* codes, int code_bytes,
+                      int64_t codes_head_stride, int64_t codes_token_stride, int64_t codes_m_stride, int64_t t0,
+                      int n_heads, int n_tokens, int d, int M, int C, int impl, million_stream_t stream) {
+    MILLION_REQUIRE(n_heads >= 0 && n_tokens >= 0, "encode: negative sizes");
+    if (n_heads == 0 || n_tokens == 0) return MILLION_OK;
+    MILLION_REQUIRE(x && cent && codes, "encode: null pointer");
+    MILLION_REQUIRE(M > 0 && d > 0 && d % M == 0 && C > 1, "encode: need d %% M == 0 and C > 1 (d=%d M=%d C=%d)", d, M, C);
+    MILLION_REQUIRE(code_bytes == 1 || code_bytes == 2, "encode: code_bytes must be 1 or 2");
+    MILLION_REQUIRE(C <= (code_bytes == 1 ? 256 : 65536), "encode: C=%d does not fit %d-byte codes", C, code_bytes);
+    return encode_dispatch(x, x_dtype, x_head_stride, cent, codes, code_bytes, codes_head_stride, codes_token_stride,
+                           codes_m_stride, t0, nullptr, 0, 0, n_heads, n_tokens, d, M, C, impl, (cudaStream_t)stream);
+}
+
+int million_pq_encode_paged(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, uint8_t* page_pool,
+                            const int64_t* page_ids, int64_t page_ids_head_stride, int page_size, int64_t t0, int n_heads,
+                            int n_tokens, int d, int M, int C, int impl, million_stream_t stream) {
+    MILLION_REQUIRE(n_heads >= 0 && n_tokens >= 0, "encode_paged: negative sizes");
+    if (n_heads == 0 || n_tokens == 0) return MILLION_OK;
+    MILLION_REQUIRE(x && cent && page_pool && page_ids, "encode_paged: null pointer");
+    MILLION_REQUIRE(M > 0 && d > 0 && d % M == 0 && C > 1 && C <= 256, "encode_paged: bad d/M/C (%d/%d/%d)", d, M, C);
+    MILLION_REQUIRE(page_size > 0, "encode_paged: page_size must be positive");
+    return encode_dispatch(x, x_dtype, x_head_stride, cent, page_pool, 1, 0, 0, 0, t0, page_ids, page_ids_head_stride,
+                           page_size, n_heads, n_tokens, d, M, C, impl, (cudaStream_t)stream);
+}
+
+int million_pq_decode(const void* codes, int code_bytes, int64_t chs, int64_t cts, int64_t cms, const void* cent, void* out,
+                      int dtype, int64_t out_head_stride, int n_heads, int n_tokens, int d, int M, int C,
+                      million_stream_t stream) {
+    MILLION_REQUIRE(n_heads >= 0 && n_tokens >= 0, "decode: negative sizes");
+    if (n_heads == 0 || n_tokens == 0) return MILLION_OK;
+    MILLION_REQUIRE(codes && cent && out, "decode: null pointer");
+    MILLION_REQUIRE(M > 0 && d % M == 0, "decode: need d %% M == 0");
+    MILLION_REQUIRE(code_bytes == 1 || code_bytes == 2, "decode: code_bytes must be 1 or 2");
+    MILLION_REQUIRE(dtype >= MILLION_F16 && dtype <= MILLION_F32, "decode: bad dtype");
+    return launch_reconstruct(codes, code_bytes, chs, cts, cms, cent, out, dtype, out_head_stride, n_heads, n_tokens, d, M, C,
+                              (cudaStream_t)stream);
+}
+
+int million_pq_decode_attn_default_splits(int bs, int nh_k, int nk) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int groups = bs * nh_k > 0 ? bs * nh_k : 1;
+    // one CTA per SM: fill the machine once, never fewer than 128 coded tokens per split
+    int s = sms / groups;
+    if (s < 1) s = 1;
+    const int max_by_len = (nk + 127) / 128;
+    if (s > max_by_len) s = max_by_len;
+    if (s < 1) s = 1;
+    return s;
+}
+
+int64_t million_pq_decode_attn_workspace_bytes(int bs, int nh, int nh_k, int d, int max_splits) {
+    const int64_t counters = ((int64_t)bs * nh_k * 4 + 255) / 256 * 256;
+    return counters + (int64_t)bs * nh * (max_splits + 1) * (d + 2) * 4;
+}
+
+int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream) {
+    MILLION_REQUIRE(p != nullptr, "attn: null params");
+    MILLION_REQUIRE(p->struct_size == sizeof(million_attn_params), "attn: struct_size %u != %zu (ABI mismatch)",
+                    p->struct_size, sizeof(million_attn_params));
+    MILLION_REQUIRE(p->io_dtype == MILLION_F16 || p->io_dtype == MILLION_BF16, "attn: io_dtype must be f16 or bf16");
+    MILLION_REQUIRE(p->bs >= 0 && p->nh > 0 && p->nh_k > 0 && p->nh % p->nh_k == 0, "attn: bad head counts");
+    MILLION_REQUIRE(p->M > 0 && p->d % p->M == 0 && p->C > 1 && p->C <= 256, "attn: bad d/M/C (%d/%d/%d)", p->d, p->M, p->C);
+    MILLION_REQUIRE(p->nk >= 0 && p->r >= 0 && p->r <= p->res_len, "attn: bad nk/r (nk=%d r=%d res_len=%d)", p->nk, p->r, p->res_len);
+    if (p->bs == 0) return MILLION_OK;
+    const bool partial_only = (p->flags & MILLION_ATTN_PARTIAL_ONLY) != 0;
+    MILLION_REQUIRE(p->q && p->k_cent && p->v_cent && p->workspace, "attn: null pointer");
+    MILLION_REQUIRE(partial_only ? (p->partial != nullptr) : (p->out != nullptr), "attn: missing output pointer");
+    MILLION_REQUIRE(p->nk == 0 || (p->k_codes && p->v_codes), "attn: null code pointer");
+    MILLION_REQUIRE(p->r == 0 || (p->k_res && p->v_res), "attn: null residual pointer");
+    MILLION_REQUIRE(p->v_layout >= MILLION_V_ROWMAJOR && p->v_layout <= MILLION_V_PAGED, "attn: bad v_layout");
+    if (p->v_layout == MILLION_V_PAGED && p->nk > 0) {
+        MILLION_REQUIRE(p->v_page_ids && p->page_size > 0, "attn: paged V needs page ids and page_size");
+        MILLION_REQUIRE((int64_t)p->n_pages * p->page_size >= p->nk, "attn: %d pages of %d < nk=%d", p->n_pages, p->page_size, p->nk);
+    }
+    if (p->nk > 0) MILLION_REQUIRE(p->k_head_stride >= (int64_t)p->nk * p->M, "attn: k_head_stride too small");
+
+    int S = p->n_splits > 0 ? p->n_splits : million_pq_decode_attn_default_splits(p->bs, p->nh_k, p->nk);
+    MILLION_REQUIRE(p->workspace_bytes >= million_pq_decode_attn_workspace_bytes(p->bs, p->nh, p->nh_k, p->d, S),
+                    "attn: workspace too small for %d splits", S);
+    MILLION_REQUIRE(((uintptr_t)p->workspace & 15) == 0, "attn: workspace must be 16-byte aligned");
+
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = p->q; a.k_codes = p->k_codes; a.v_codes = p->v_codes; a.v_page_ids = p->v_page_ids;
+    a.k_cent = p->k_cent; a.v_cent = p->v_cent; a.k_res = p->k_res; a.v_res = p->v_res;
+    a.out = p->out; a.partial_out = partial_only ? p->partial : nullptr;
+    a.counters = reinterpret_cast<int*>(p->workspace);
+    a.parts = reinterpret_cast<float*>(reinterpret_cast<char*>(p->workspace) + ((int64_t)p->bs * p->nh_k * 4 + 255) / 256 * 256);
+    a.k_head_stride = p->k_head_stride; a.v_head_stride = p->v_head_stride; a.v_ld = p->v_ld;
+    a.bs = p->bs; a.nh = p->nh; a.nh_k = p->nh_k; a.d = p->d; a.M = p->M; a.C = p->C; a.nk = p->nk; a.r = p->r;
+    a.res_len = p->res_len; a.v_layout = p->v_layout; a.page_size = p->page_size; a.n_pages = p->n_pages;
+    a.n_splits = S;
+    const int units = (p->nk + 15) / 16;
+    a.units_per_split = (units + S - 1) / S;
+    if (a.units_per_split < 1) a.units_per_split = 1;
+    a.scale_log2 = kLog2e / sqrtf((float)p->d);
+
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->impl == MILLION_IMPL_GENERIC) return launch_attn_generic(a, p->io_dtype, st);
+    if (p->impl == MILLION_IMPL_FAST) return launch_attn_fast(a, p->io_dtype, st, false);
+    if (launch_attn_fast(a, p->io_dtype, st, true) == MILLION_OK) return launch_attn_fast(a, p->io_dtype, st, false);
+    return launch_attn_generic(a, p->io_dtype, st);
+}
+
+int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, million_stream_t stream) {
+    MILLION_REQUIRE(parts && out && n_parts > 0 && n_rows >= 0 && d > 0, "lse_merge: bad arguments");
+    MILLION_REQUIRE(io_dtype >= MILLION_F16 && io_dtype <= MILLION_F32, "lse_merge: bad dtype");
+    return launch_lse_merge(parts, n_parts, n_rows, d, out, io_dtype, (cudaStream_t)stream);
+}
+
+int million_window_append(void* k_win, void* v_win, int64_t win_head_stride, const void* k_src, const void* v_src,
+                          int64_t src_head_stride, int n_heads, int r0, int n, int d, int dtype, million_stream_t stream) {
+    MILLION_REQUIRE(k_win && v_win && k_src && v_src, "window_append: null pointer");
+    MILLION_REQUIRE(n_heads >= 0 && r0 >= 0 && n >= 0 && d > 0, "window_append: bad sizes");
+    const int eb = elem_bytes(dtype);
+    return launch_rows_copy2(k_win, v_win, win_head_stride * eb, (int64_t)r0 * d * eb, k_src, v_src, src_head_stride * eb, 0,
+                             n_heads, (int64_t)n * d * eb, (cudaStream_t)stream);
+}
+
+int million_window_shift(void* k_win, void* v_win, int64_t win_head_stride, int n_heads, int shift, int rem, int d, int dtype,
+                         million_stream_t stream) {
+    MILLION_REQUIRE(k_win && v_win, "window_shift: null pointer");
+    MILLION_REQUIRE(n_heads >= 0 && shift > 0 && rem >= 0 && d > 0, "window_shift: bad sizes");
+    const int eb = elem_bytes(dtype);
+    // chunks of at most `shift` rows never overlap their own source; stream order keeps them sequential
+    for (int done = 0; done < rem; done += shift) {
+        const int n = (rem - done) < shift ? (rem - done) : shift;
+        int rc = launch_rows_copy2(k_win, v_win, win_head_stride * eb, (int64_t)done * d * eb, k_win, v_win, win_head_stride * eb,
+                                   (int64_t)(done + shift) * d * eb, n_heads, (int64_t)n * d * eb, (cudaStream_t)stream);
+        if (rc != MILLION_OK) return rc;
+    }
+    return MILLION_OK;
+}
+
+}  // extern "C"

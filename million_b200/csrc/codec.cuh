@@ -1,0 +1,33 @@
+// codec.cuh — destination descriptor shared by the encoders (row-major / transposed / paged code stores).
+#pragma once
+#include "common.cuh"
+
+namespace million {
+
+struct CodeDst {
+    void* base;
+    int code_bytes;
+    int64_t head_stride, token_stride, m_stride, t0;  // elements
+    const int64_t* page_ids;                          // non-null => paged pool (pages, M, page_size) uint8
+    int64_t page_ids_head_stride;
+    int page_size, M;
+
+    __device__ __forceinline__ int64_t offset(int head, int t, int m) const {
+        if (page_ids) {
+            const int64_t tt = t0 + t;
+            const int64_t page = page_ids[head * page_ids_head_stride + tt / page_size];
+            return (page * M + m) * page_size + tt % page_size;
+        }
+        return head * head_stride + (t0 + t) * token_stride + m * m_stride;
+    }
+    __device__ __forceinline__ void put(int head, int t, int m, int code) const {
+        const int64_t off = offset(head, t, m);
+        if (code_bytes == 1) reinterpret_cast<uint8_t*>(base)[off] = (uint8_t)code;
+        else reinterpret_cast<uint16_t*>(base)[off] = (uint16_t)code;
+    }
+};
+
+int launch_encode_generic(const void* x, int x_dtype, int64_t xhs, const float* cent, const CodeDst& dst, int n_heads,
+                          int n_tokens, int d, int M, int C, cudaStream_t stream);
+
+}  // namespace million

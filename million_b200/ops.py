@@ -1,0 +1,222 @@
+"""torch-tensor front end of the C ABI: device pointers, strides and the current CUDA stream go straight
+into libmillion_b200.so.  torch is used for memory and streams only."""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float16: L.MILLION_F16, torch.bfloat16: L.MILLION_BF16, torch.float32: L.MILLION_F32}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype if isinstance(t, torch.Tensor) else t]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype if isinstance(t, torch.Tensor) else t}")
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("million_b200 ops run on CUDA tensors only (there is no CPU path)")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+# ---------------------------------------------------------------------------------------------- encode
+
+
+def _x_view(X):
+    """(bs, nh_k, n, d) with contiguous rows -> (ptr tensor, head stride in elements)."""
+    bs, nh, n, d = X.shape
+    if n and (X.stride(3) != 1 or X.stride(2) != d or (nh > 1 and bs > 1 and X.stride(0) != nh * X.stride(1))):
+        X = X.contiguous()
+    hs = X.stride(1) if nh > 1 else (X.stride(0) if bs > 1 else n * d)
+    return X, hs
+
+
+def pq_encode_into(X, cent_f32, codes, *, t0=0, layout="rowmajor", impl=L.IMPL_AUTO):
+    """Encode X (bs, nh_k, n, d) and write the codes at token offset t0 of a preallocated cache.
+    layout 'rowmajor': codes (bs, nh_k, cap, M); 'transposed': codes (bs, nh_k, M, cap)."""
+    _need_cuda(X, cent_f32, codes)
+    bs, nh, n, d = X.shape
+    M, C, dm = cent_f32.shape
+    assert cent_f32.dtype == torch.float32 and cent_f32.is_contiguous() and M * dm == d
+    X, xhs = _x_view(X)
+    if layout == "rowmajor":
+        assert codes.shape[0] == bs and codes.shape[1] == nh and codes.shape[3] == M and codes.stride(3) == 1
+        hs, ts, ms = codes.stride(1), codes.stride(2), 1
+        assert bs == 1 or codes.stride(0) == nh * codes.stride(1)
+    else:
+        assert codes.shape[0] == bs and codes.shape[1] == nh and codes.shape[2] == M and codes.stride(3) == 1
+        hs, ts, ms = codes.stride(1), 1, codes.stride(2)
+        assert bs == 1 or codes.stride(0) == nh * codes.stride(1)
+    L.check(L.lib().million_pq_encode(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(codes), codes.element_size(),
+                                      hs, ts, ms, t0, bs * nh, n, d, M, C, impl, _stream(X)))
+    return codes
+
+
+def pq_encode(X, cent_f32, *, out_dtype=torch.uint8, impl=L.IMPL_AUTO):
+    """sa_encode_4d_keops semantics: (bs, nh_k, n, d) -> (bs, nh_k, n, M) codes."""
+    bs, nh, n, d = X.shape
+    M = cent_f32.shape[0]
+    store = torch.uint8 if out_dtype == torch.uint8 else torch.int16
+    codes = torch.empty(bs, nh, n, M, dtype=store, device=X.device)
+    pq_encode_into(X, cent_f32, codes, impl=impl)
+    if store != out_dtype:
+        codes = (codes.to(torch.int32) & 0xFFFF).to(out_dtype)
+    return codes
+
+
+def pq_encode_paged(X, cent_f32, page_pool, page_ids, *, t0, impl=L.IMPL_AUTO):
+    """Encode X (bs, nh_k, n, d) into pool (pages, M, page_size) through page_ids (bs, nh_k, n_pages) int64."""
+    _need_cuda(X, cent_f32, page_pool, page_ids)
+    bs, nh, n, d = X.shape
+    M, C, dm = cent_f32.shape
+    assert page_pool.dtype == torch.uint8 and page_pool.is_contiguous() and page_pool.shape[1] == M
+    assert page_ids.dtype == torch.int64 and page_ids.is_contiguous() and page_ids.shape[:2] == (bs, nh)
+    X, xhs = _x_view(X)
+    L.check(L.lib().million_pq_encode_paged(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(page_pool), _ptr(page_ids),
+                                            page_ids.shape[2], page_pool.shape[2], t0, bs * nh, n, d, M, C, impl, _stream(X)))
+
+
+def pq_decode(codes, cent):
+    """sa_decode_4d semantics: codes (bs, nh_k, n, M) [any strides with unit M stride], cent (M, C, d_m) -> (bs, nh_k, n, d)."""
+    _need_cuda(codes, cent)
+    bs, nh, n, M = codes.shape
+    Mc, C, dm = cent.shape
+    cent = cent.contiguous()
+    if codes.dtype not in (torch.uint8, torch.int16, torch.uint16):
+        codes = codes.to(torch.int16)
+    if n and (codes.stride(3) != 1 or (bs > 1 and nh > 1 and codes.stride(0) != nh * codes.stride(1))):
+        codes = codes.contiguous()
+    out = torch.empty(bs, nh, n, M * dm, dtype=cent.dtype, device=codes.device)
+    hs = codes.stride(1) if nh > 1 else (codes.stride(0) if bs > 1 else n * M)
+    L.check(L.lib().million_pq_decode(_ptr(codes), codes.element_size(), hs, codes.stride(2) if n else M, 1,
+                                      _ptr(cent), _ptr(out), _dt(cent), n * M * dm, bs * nh, n, M * dm, M, C, _stream(codes)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- attention
+
+_workspaces = {}
+
+
+def attn_workspace(device, bs, nh, nh_k, d, splits):
+    """Zero-initialised scratch, cached per device and grown on demand (the kernel leaves its counters zero)."""
+    need = L.lib().million_pq_decode_attn_workspace_bytes(bs, nh, nh_k, d, splits)
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def default_splits(bs, nh_k, nk):
+    return L.lib().million_pq_decode_attn_default_splits(bs, nh_k, nk)
+
+
+def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=None, v_layout=L.V_ROWMAJOR,
+                   v_page_ids=None, page_size=0, out=None, partial=None, n_splits=0, impl=L.IMPL_AUTO, workspace=None):
+    """One decode-attention call (include/million_b200.h: million_pq_decode_attn).
+
+    q (bs, nh, 1, d) | (bs, nh, d); k_codes (bs, nh_k, >=nk, M) uint8 (head stride taken from the tensor);
+    v_codes: rowmajor (bs, nh_k, >=nk, M) | transposed (bs, nh_k, M, >=nk) | paged pool (pages, M, page_size);
+    k_res/v_res (bs, nh_k, Lt, d).  Returns (bs, nh, 1, d) in q's dtype, or fills `partial` (bs, nh, d+2) fp32.
+    """
+    _need_cuda(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res)
+    bs, nh = q.shape[0], q.shape[1]
+    d = q.shape[-1]
+    M, C, dm = k_cent.shape
+    nh_k = k_res.shape[1] if k_res is not None else k_codes.shape[1]
+    if nk is None:
+        nk = k_codes.shape[2]
+    assert q.is_contiguous() and k_cent.is_contiguous() and v_cent.is_contiguous()
+    assert k_cent.dtype == q.dtype and v_cent.dtype == q.dtype, "centroids must be in the query dtype"
+    p = L.AttnParams()
+    p.struct_size = ctypes.sizeof(L.AttnParams)
+    p.io_dtype, p.impl, p.flags = _dt(q), impl, (L.ATTN_PARTIAL_ONLY if partial is not None else 0)
+    p.bs, p.nh, p.nh_k, p.d, p.M, p.C, p.nk, p.r = bs, nh, nh_k, d, M, C, nk, r
+    p.q = q.data_ptr()
+    if nk:
+        assert k_codes.dtype == torch.uint8 and k_codes.stride(3) == 1 and k_codes.stride(2) == M
+        assert bs == 1 or k_codes.stride(0) == nh_k * k_codes.stride(1)
+        p.k_codes, p.k_head_stride = k_codes.data_ptr(), (k_codes.stride(1) if nh_k > 1 or bs > 1 else k_codes.shape[2] * M)
+        p.v_codes = v_codes.data_ptr()
+        if v_layout == L.V_ROWMAJOR:
+            assert v_codes.stride(3) == 1 and v_codes.stride(2) == M
+            p.v_head_stride = v_codes.stride(1) if nh_k > 1 or bs > 1 else v_codes.shape[2] * M
+        elif v_layout == L.V_TRANSPOSED:
+            assert v_codes.stride(3) == 1
+            p.v_head_stride, p.v_ld = v_codes.stride(1), v_codes.stride(2)
+        else:
+            assert v_codes.is_contiguous() and v_page_ids.dtype == torch.int64 and v_page_ids.is_contiguous()
+            p.v_page_ids, p.n_pages, p.page_size = v_page_ids.data_ptr(), v_page_ids.shape[2], page_size or v_codes.shape[2]
+    p.v_layout = v_layout
+    p.k_cent, p.v_cent = k_cent.data_ptr(), v_cent.data_ptr()
+    p.res_len = k_res.shape[2] if k_res is not None else 0
+    if r:
+        assert k_res.dtype == q.dtype and v_res.dtype == q.dtype
+        # rows must be contiguous; a [:, :, :r] slice of a larger window is taken in place (res_len from the stride)
+        def rows_ok(t):
+            return t.stride(3) == 1 and t.stride(2) == d and t.stride(1) % d == 0 and (bs == 1 or t.stride(0) == nh_k * t.stride(1))
+        if not (rows_ok(k_res) and rows_ok(v_res) and k_res.stride(1) == v_res.stride(1)):
+            k_res, v_res = k_res.contiguous(), v_res.contiguous()
+        p.res_len = k_res.stride(1) // d if (nh_k > 1 or bs > 1) else max(k_res.shape[2], r)
+        p.k_res, p.v_res = k_res.data_ptr(), v_res.data_ptr()
+    splits = n_splits or default_splits(bs, nh_k, nk)
+    ws = workspace if workspace is not None else attn_workspace(q.device, bs, nh, nh_k, d, splits)
+    p.workspace, p.workspace_bytes, p.n_splits = ws.data_ptr(), ws.numel(), splits
+    if partial is not None:
+        assert partial.dtype == torch.float32 and partial.is_contiguous() and partial.numel() == bs * nh * (d + 2)
+        p.partial = partial.data_ptr()
+        ret = partial
+    else:
+        if out is None:
+            out = torch.empty(bs, nh, 1, d, dtype=q.dtype, device=q.device)
+        assert out.is_contiguous() and out.dtype == q.dtype
+        p.out = out.data_ptr()
+        ret = out
+    L.check(L.lib().million_pq_decode_attn(ctypes.byref(p), _stream(q)))
+    return ret
+
+
+def lse_merge(parts, d, out_dtype):
+    """parts (n_parts, rows, d+2) fp32 -> (rows, d) out_dtype."""
+    _need_cuda(parts)
+    assert parts.dtype == torch.float32 and parts.is_contiguous()
+    n_parts, rows = parts.shape[0], parts.shape[1]
+    out = torch.empty(rows, d, dtype=out_dtype, device=parts.device)
+    L.check(L.lib().million_lse_merge(_ptr(parts), n_parts, rows, d, _ptr(out), _dt(out), _stream(parts)))
+    return out
+
+
+def window_append(k_win, v_win, k_new, v_new, r0):
+    """window[:, :, r0:r0+n] = new for K and V in one launch (pq_utils.py:304-311)."""
+    _need_cuda(k_win, v_win, k_new, v_new)
+    bs, nh, Lt, d = k_win.shape
+    n = k_new.shape[2]
+    assert r0 + n <= Lt
+    if not (k_new.stride(3) == 1 and k_new.stride(2) == d and (bs == 1 or nh == 1 or k_new.stride(0) == nh * k_new.stride(1))):
+        k_new = k_new.contiguous()
+    if not (v_new.stride(3) == 1 and v_new.stride(2) == d and (bs == 1 or nh == 1 or v_new.stride(0) == nh * v_new.stride(1))):
+        v_new = v_new.contiguous()
+    if k_new.stride(1) != v_new.stride(1) or k_new.stride(0) != v_new.stride(0):
+        k_new, v_new = k_new.contiguous(), v_new.contiguous()
+    shs = k_new.stride(1) if nh > 1 else (k_new.stride(0) if bs > 1 else n * d)
+    L.check(L.lib().million_window_append(_ptr(k_win), _ptr(v_win), Lt * d, _ptr(k_new), _ptr(v_new), shs, bs * nh, r0, n, d,
+                                          _dt(k_win), _stream(k_win)))
+
+
+def window_shift(k_win, v_win, shift, rem):
+    _need_cuda(k_win, v_win)
+    bs, nh, Lt, d = k_win.shape
+    L.check(L.lib().million_window_shift(_ptr(k_win), _ptr(v_win), Lt * d, bs * nh, shift, rem, d, _dt(k_win), _stream(k_win)))

@@ -1,0 +1,412 @@
+"""B200-native counterpart of the reference's scripts/utils/pq_utils.py — same names, arguments and
+semantics; different machinery:
+
+  * `sa_encode_4d_keops` / `sa_encode_4d` / `sa_decode_4d` call the CUDA library (pq_utils.py:410-540),
+  * `DynamicPQCache` keeps codes in a PREALLOCATED, geometrically grown cache and appends in place
+    (the reference re-allocates the whole cache with torch.cat on every flush, pq_utils.py:145-146,
+    297-298), and quantizes a full window ASYNCHRONOUSLY on a side stream as soon as it fills
+    (the reference encodes synchronously inside the next decode step, pq_utils.py:287-302),
+  * `KernelRegistry` resolves the same kernel names (pq_utils.py:64) through `million_b200.bindings`.
+
+There is no CPU path: every compute entry point needs CUDA tensors and the built extension.
+"""
+import torch
+
+from . import _lib as L
+from . import bindings as _bindings
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+
+
+def l2Ns(l):
+    """Split-count heuristic of the reference (pq_utils.py:8-22).  Only used to form kernel NAMES; the
+    B200 kernel picks its own split count from the SM count."""
+    if l > 2048:
+        return 32
+    elif l > 256:
+        return 16
+    elif l > 128:
+        return 4
+    elif l > 64:
+        return 2
+    else:
+        return 1
+
+
+def scalarTypeToStr(scalar_t):
+    """pq_utils.py:24-30, plus bf16 (new)."""
+    if scalar_t == torch.float32:
+        return 'f32'
+    elif scalar_t == torch.float16:
+        return 'f16'
+    elif scalar_t == torch.bfloat16:
+        return 'bf16'
+    else:
+        raise ValueError(f"Unknown scalar type: {scalar_t}")
+
+
+def nbits2dtype(nbits):
+    """pq_utils.py:542-552."""
+    if nbits <= 8:
+        return torch.uint8
+    elif nbits <= 16:
+        return torch.uint16
+    elif nbits <= 32:
+        return torch.uint32
+    elif nbits <= 64:
+        return torch.uint64
+    else:
+        raise ValueError("nbits must be <= 64")
+
+
+class Singleton(type):
+    """Per-class singleton metaclass (scripts/utils/Singleton.py:3-27).  `has_instance` is per class here;
+    the reference's is global across every singleton class — not replicated."""
+    _instances = {}
+
+    def __call__(cls, *args, **kwargs):
+        if cls not in Singleton._instances:
+            Singleton._instances[cls] = super().__call__(*args, **kwargs)
+        return Singleton._instances[cls]
+
+    def has_instance(cls):
+        return cls in Singleton._instances
+
+    def clear_instance(cls=None):
+        if cls is None or cls is Singleton:
+            Singleton._instances.clear()
+        else:
+            Singleton._instances.pop(cls, None)
+
+
+# ------------------------------------------------------------------------------------------------ codec
+
+
+def _cent_f32(C):
+    if C.dim() != 3:
+        raise NotImplementedError("per-head codebooks (5-D C) are not used by the reference's callers")
+    return C.to(torch.float32).contiguous()
+
+
+def sa_encode_4d_keops(X, C, target_dtype=torch.uint8):
+    """Nearest-codeword indices, (bs, num_heads, n, d) x (M, c, d//M) -> (bs, num_heads, n, M)
+    (pq_utils.py:451-499).  fp32 squared-L2 arg-min on the GPU; lowest index on ties."""
+    return ops.pq_encode(X, _cent_f32(C), out_dtype=target_dtype)
+
+
+def sa_encode_4d(X, C, target_dtype=torch.uint8):
+    """pq_utils.py:410-449 (torch.cdist twin).  Same arg-min; the sqrt of cdist is monotone, so the codes
+    agree with sa_encode_4d_keops except on float near-ties of the reference's own arithmetic."""
+    return ops.pq_encode(X, _cent_f32(C), out_dtype=target_dtype)
+
+
+def sa_decode_4d(codes, C):
+    """Reconstruct (bs, num_heads, n, M) codes -> (bs, num_heads, n, d) in C's dtype (pq_utils.py:501-540)."""
+    if C.dim() != 3:
+        raise NotImplementedError("per-head codebooks (5-D C) are not used by the reference's callers")
+    return ops.pq_decode(codes, C)
+
+
+# ------------------------------------------------------------------------------------------------ registry
+
+
+class KernelRegistry:
+    """pq_utils.py:32-96: resolves `flash_decoding_allocated_buffer_<...>` by name and returns a closure that
+    hides the partial buffers.  The partial buffers are still allocated (attribute compatibility,
+    pq_utils.py:73-77) but the B200 kernel keeps its fp32 partials in its own workspace."""
+
+    def __init__(self, *, M=64, d=128, nbits=8, nh=32, scalar_t=torch.float32, bs=1):
+        self.kernels = {}
+        self.partial_out_buffers = {}
+        self.partial_lse_buffers = {}
+        self.M, self.d, self.nbits, self.nh, self.scalar_t, self.bs = M, d, nbits, nh, scalar_t, bs
+
+    def get_kernel(self, l=4096):
+        Ns = l2Ns(l)
+        if Ns not in self.kernels:
+            self.kernels[Ns] = self.get_custom_kernel_with_allocated_buffer(l)
+        return self.kernels[Ns]
+
+    def get_custom_kernel_with_allocated_buffer(self, l=4096):
+        M, d, nbits, nh, scalar_t = self.M, self.d, self.nbits, self.nh, self.scalar_t
+        if nbits != 8:
+            raise NotImplementedError("Only uint8 code type is supported for now")
+        Ns = l2Ns(l)
+        scalar_str = scalarTypeToStr(scalar_t)
+        fname = f"flash_decoding_allocated_buffer_{scalar_str}u8_Ns{Ns}Lt{d}d{d}M{M}C{2**nbits}"
+        try:
+            func = getattr(_bindings, fname)
+        except Exception as e:
+            print(f"{fname} not available in million_b200.bindings (supported scalars: f16, bf16).")
+            raise e
+        partial_out_buffer = torch.empty(self.bs, nh, Ns + 1, d, dtype=scalar_t, device='cuda')
+        partial_lse_buffer = torch.empty(self.bs, nh, Ns + 1, dtype=scalar_t, device='cuda')
+        self.partial_out_buffers[Ns] = partial_out_buffer
+        self.partial_lse_buffers[Ns] = partial_lse_buffer
+
+        def flash_decoding(query, key_codes, value_codes, key_cents, value_cents, key_residuals, value_residuals, r):
+            return func(query, key_codes, value_codes, key_cents, value_cents, key_residuals, value_residuals, r,
+                        partial_out_buffer, partial_lse_buffer)
+
+        return flash_decoding
+
+
+# ------------------------------------------------------------------------------------------------ cache
+
+
+class _CodeStore:
+    """Preallocated (bs, nh_k, cap, M) code cache with amortised-doubling growth and in-place append."""
+
+    def __init__(self, bs, nh_k, M, dtype, device, transposed=False):
+        self.bs, self.nh_k, self.M, self.dtype, self.device, self.transposed = bs, nh_k, M, dtype, device, transposed
+        self.cap, self.len = 0, 0
+        self.buf = self._alloc(0)
+
+    def _alloc(self, cap):
+        shape = (self.bs, self.nh_k, self.M, cap) if self.transposed else (self.bs, self.nh_k, cap, self.M)
+        return torch.zeros(shape, dtype=self.dtype, device=self.device)
+
+    def reserve(self, n):
+        if n <= self.cap:
+            return
+        cap = max(n, 2 * self.cap, 1024)
+        cap = (cap + 127) // 128 * 128
+        new = self._alloc(cap)
+        if self.len:
+            if self.transposed:
+                new[:, :, :, :self.len] = self.buf[:, :, :, :self.len]
+            else:
+                new[:, :, :self.len] = self.buf[:, :, :self.len]
+        self.buf, self.cap = new, cap
+
+    def view(self, n=None):
+        n = self.len if n is None else n
+        return self.buf[:, :, :, :n] if self.transposed else self.buf[:, :, :n]
+
+
+class DynamicPQCache(metaclass=Singleton):
+    """pq_utils.py:98-408.  Same constructor, attributes and methods.
+
+    key_cache[layer] / value_cache[layer] are views (bs, nh_k, T, M) into preallocated stores.
+    `async_flush=True` (default) starts quantizing a full window on a side stream right after the step
+    that filled it; the next step only waits on an event.  Results are identical either way."""
+
+    def __init__(self, *, bs, nh, num_key_value_heads, M, layer_num, dtype=torch.uint8, nbits=8, d=128,
+                 scalar_t=torch.float32, async_flush=True, device='cuda'):
+        self.bs, self.nh, self.num_key_value_heads, self.M = bs, nh, num_key_value_heads, M
+        self.layer_num, self.dtype, self.nbits, self.d, self.scalar_t = layer_num, dtype, nbits, d, scalar_t
+        self.device = torch.device(device)
+        self.async_flush = async_flush
+        self.max_residual_length = d  # Lt = d (pq_utils.py:111)
+        self.registery = KernelRegistry(M=M, d=d, nbits=nbits, nh=nh, scalar_t=scalar_t, bs=bs)
+        self._side = None
+        self.init_cache()
+
+    # ---- storage
+    def _new_store(self, transposed=False):
+        return _CodeStore(self.bs, self.num_key_value_heads, self.M, self.dtype, self.device, transposed)
+
+    def init_cache(self):
+        """pq_utils.py:116-138."""
+        if not self.device.type == 'cuda':
+            raise RuntimeError("DynamicPQCache needs a CUDA device (no CPU path)")
+        self._k = [self._new_store() for _ in range(self.layer_num)]
+        self._v = [self._new_store() for _ in range(self.layer_num)]
+        z = lambda: torch.zeros((self.bs, self.num_key_value_heads, self.max_residual_length, self.d),
+                                dtype=self.scalar_t, device=self.device)
+        self.key_residual_cache = [z() for _ in range(self.layer_num)]
+        self.value_residual_cache = [z() for _ in range(self.layer_num)]
+        self.seen_tokens = [0 for _ in range(self.layer_num)]
+        self.residualed_tokens = [0 for _ in range(self.layer_num)]
+        self._pending = [None for _ in range(self.layer_num)]   # (event, n_tokens) of an in-flight async flush
+
+    @property
+    def key_cache(self):
+        return [s.view() for s in self._k]
+
+    @property
+    def value_cache(self):
+        return [s.view() for s in self._v]
+
+    def set_cent(self, key_cent, value_cent):
+        """cent is of shape (M, c, d//M) (pq_utils.py:149-159).  fp32 copies feed the encoder (the reference
+        casts per call, pq_utils.py:484)."""
+        if key_cent is value_cent:
+            self._cent = key_cent.contiguous()
+            self.key_cent = self._cent
+            self.value_cent = self._cent
+        else:
+            self.key_cent = key_cent.contiguous()
+            self.value_cent = value_cent.contiguous()
+        self._key_cent_f32 = self.key_cent.to(device=self.device, dtype=torch.float32).contiguous()
+        self._value_cent_f32 = self.value_cent.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _attn_cents(self, dtype):
+        """Centroids in the query dtype for the attention kernel (main_pq.py:258-260 casts them to the model dtype)."""
+        if getattr(self, '_attn_dtype', None) != dtype:
+            self._kc_attn = self.key_cent.to(device=self.device, dtype=dtype).contiguous()
+            self._vc_attn = self.value_cent.to(device=self.device, dtype=dtype).contiguous()
+            self._attn_dtype = dtype
+        return self._kc_attn, self._vc_attn
+
+    # ---- code append
+    def _encode_append(self, key_states, value_states, layer_idx, count_seen=True):
+        if self._pending[layer_idx] is not None:
+            self._finish_async_flush(layer_idx)
+        n = key_states.size(2)
+        ks, vs = self._k[layer_idx], self._v[layer_idx]
+        ks.reserve(ks.len + n)
+        vs.reserve(vs.len + n)
+        ops.pq_encode_into(key_states, self._key_cent_f32, ks.buf, t0=ks.len)
+        ops.pq_encode_into(value_states, self._value_cent_f32, vs.buf, t0=vs.len,
+                           layout="transposed" if vs.transposed else "rowmajor")
+        ks.len += n
+        vs.len += n
+        if count_seen:
+            self.seen_tokens[layer_idx] += n
+        return ks.view()[:, :, ks.len - n:], n
+
+    def cat_codes(self, key_codes, value_codes, layer_idx):
+        """pq_utils.py:140-147 — kept for API compatibility: appends ready-made codes in place."""
+        if self._pending[layer_idx] is not None:
+            self._finish_async_flush(layer_idx)
+        n = key_codes.size(2)
+        ks, vs = self._k[layer_idx], self._v[layer_idx]
+        ks.reserve(ks.len + n)
+        vs.reserve(vs.len + n)
+        ks.buf[:, :, ks.len:ks.len + n] = key_codes
+        vs.buf[:, :, vs.len:vs.len + n] = value_codes
+        ks.len += n
+        vs.len += n
+        self.seen_tokens[layer_idx] += n
+
+    # ---- torch-PQ path
+    def update(self, key_states, value_states, layer_idx, distort_recent=False):
+        """pq_utils.py:166-220."""
+        assert hasattr(self, 'key_cent') and hasattr(self, 'value_cent')
+        past_length = self._k[layer_idx].len
+        if distort_recent:
+            self._encode_append(key_states, value_states, layer_idx)
+            return sa_decode_4d(self.key_cache[layer_idx], self.key_cent), sa_decode_4d(self.value_cache[layer_idx], self.value_cent)
+        if past_length > 0:
+            past_key_states = sa_decode_4d(self.key_cache[layer_idx], self.key_cent)
+            past_value_states = sa_decode_4d(self.value_cache[layer_idx], self.value_cent)
+        self._encode_append(key_states, value_states, layer_idx)
+        if past_length > 0:
+            key_states = torch.cat([past_key_states.to(key_states.dtype), key_states], dim=2)
+            value_states = torch.cat([past_value_states.to(value_states.dtype), value_states], dim=2)
+        return key_states, value_states
+
+    # ---- prefill
+    def _prefill_attention(self, query_states, key_states, value_states):
+        from torch.nn.functional import scaled_dot_product_attention as sdpa
+        return sdpa(query_states, key_states, value_states, is_causal=True,
+                    enable_gqa=query_states.size(1) != key_states.size(1))
+
+    def prefill(self, query_states, key_states, value_states, layer_idx, distort_recent=False):
+        """pq_utils.py:222-260: quantize ALL prefill tokens, then causal SDPA on the fp16 (or, with
+        distort_recent, the reconstructed) K/V.  GQA is handled inside SDPA instead of repeat_kv."""
+        n = key_states.size(2)
+        self._encode_append(key_states, value_states, layer_idx)
+        if distort_recent is True:
+            ks, vs = self._k[layer_idx], self._v[layer_idx]
+            key_states = sa_decode_4d(ks.view()[:, :, ks.len - n:], self.key_cent.to(key_states.dtype))
+            vview = vs.view()[:, :, :, vs.len - n:].transpose(2, 3) if vs.transposed else vs.view()[:, :, vs.len - n:]
+            value_states = sa_decode_4d(vview, self.value_cent.to(value_states.dtype))
+        return self._prefill_attention(query_states, key_states, value_states)
+
+    def residual_attention(self, query_states, layer_idx):
+        """pq_utils.py:262-279 (deprecated in the reference: done by the kernel).  Kept for parity checks."""
+        key_states = self.key_residual_cache[layer_idx]
+        value_states = self.value_residual_cache[layer_idx]
+        G = self.nh // self.num_key_value_heads
+        k = key_states.repeat_interleave(G, dim=1).float()
+        v = value_states.repeat_interleave(G, dim=1).float()
+        S = (self.d ** -0.5) * query_states.float() @ k.transpose(-2, -1)
+        S[:, :, :, self.residualed_tokens[layer_idx]:] = float('-inf')
+        out = torch.softmax(S, dim=-1) @ v
+        lse = torch.logsumexp(S, dim=-1, keepdim=False)
+        return out, lse
+
+    # ---- flush machinery
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def _flush_window(self, layer_idx, n):
+        """Encode rows [0, n) of the window and append them (pq_utils.py:288-301).  seen_tokens already counts them."""
+        self._encode_append(self.key_residual_cache[layer_idx][:, :, :n], self.value_residual_cache[layer_idx][:, :, :n],
+                            layer_idx, count_seen=False)
+
+    def _start_async_flush(self, layer_idx, n):
+        """Launch the flush of a full window on the side stream; the code stores are grown on the main stream
+        first so the side stream never allocates memory the main stream is using."""
+        ks, vs = self._k[layer_idx], self._v[layer_idx]
+        ks.reserve(ks.len + n)
+        vs.reserve(vs.len + n)
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_stream()
+        side.wait_stream(main)                      # window rows are complete, caches are allocated
+        with torch.cuda.stream(side):
+            ops.pq_encode_into(self.key_residual_cache[layer_idx][:, :, :n], self._key_cent_f32, ks.buf, t0=ks.len)
+            ops.pq_encode_into(self.value_residual_cache[layer_idx][:, :, :n], self._value_cent_f32, vs.buf, t0=vs.len,
+                               layout="transposed" if vs.transposed else "rowmajor")
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self._pending[layer_idx] = (ev, n)
+
+    def _finish_async_flush(self, layer_idx):
+        ev, n = self._pending[layer_idx]
+        torch.cuda.current_stream(self.device).wait_event(ev)   # device-side wait; the host does not block
+        self._k[layer_idx].len += n
+        self._v[layer_idx].len += n
+        self._pending[layer_idx] = None
+
+    # ---- decode
+    def decoding(self, query_states, key_states, value_states, layer_idx):
+        """pq_utils.py:281-327: flush a full window, append the new token to the window, run the kernel."""
+        if self.residualed_tokens[layer_idx] == self.max_residual_length:
+            if self._pending[layer_idx] is not None:
+                self._finish_async_flush(layer_idx)
+            else:
+                self._flush_window(layer_idx, self.max_residual_length)
+            self.residualed_tokens[layer_idx] = 0
+
+        r = self.residualed_tokens[layer_idx]
+        n = key_states.size(2)
+        ops.window_append(self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], key_states, value_states, r)
+        self.residualed_tokens[layer_idx] += n
+        self.seen_tokens[layer_idx] += n
+
+        kernel = self.registery.get_kernel(l=self.seen_tokens[layer_idx])
+        kc, vc = self._attn_cents(query_states.dtype)
+        out = kernel(query_states, self._k[layer_idx].view(), self._v[layer_idx].view(), kc, vc,
+                     self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
+                     self.residualed_tokens[layer_idx])
+        if self.async_flush and self.residualed_tokens[layer_idx] == self.max_residual_length:
+            self._start_async_flush(layer_idx, self.max_residual_length)
+        return out
+
+    # ---- size properties (pq_utils.py:383-408)
+    @property
+    def pq_cache_size(self):
+        return sum(s.len * self.bs * self.num_key_value_heads * self.M * s.buf.element_size() for s in self._k + self._v)
+
+    @property
+    def codebook_size(self):
+        if hasattr(self, '_cent'):
+            return self._cent.numel() * self._cent.element_size()
+        return (self.key_cent.numel() * self.key_cent.element_size()
+                + self.value_cent.numel() * self.value_cent.element_size())
+
+    @property
+    def residual_cache_size(self):
+        return sum(c.numel() * c.element_size() for c in self.key_residual_cache + self.value_residual_cache)
+
+    @property
+    def registry_size(self):
+        return (sum(b.numel() * b.element_size() for b in self.registery.partial_out_buffers.values())
+                + sum(b.numel() * b.element_size() for b in self.registery.partial_lse_buffers.values()))

@@ -1,0 +1,290 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (million_b200.ops / .bindings), against the
+CPU oracle (oracle/) on the same seeded inputs and against the committed golden fixtures.
+
+Bars (BASELINE.json north_star): codes bit-exact; attention max-abs 2e-3 / rel 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 2e-3, 1e-2   # north_star tolerance for fp16/bf16 I/O with fp32 accumulation
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+@pytest.fixture(scope="module")
+def M():
+    import million_b200.ops as ops
+    from million_b200 import _lib
+    _lib.lib()
+    return ops
+
+
+def impls():
+    from million_b200 import _lib as L
+    return [L.IMPL_GENERIC, L.IMPL_FAST]
+
+
+# ------------------------------------------------------------------------------------------------ encode
+
+
+@pytest.mark.parametrize("i", range(5))
+@pytest.mark.parametrize("impl", [1, 2])
+def test_encode_golden_bit_exact(M, golden, i, impl):
+    from million_b200 import _lib as L
+    X, cent = golden[f"enc{i}_X"], golden[f"enc{i}_cent"]
+    try:
+        got = M.pq_encode(dev(X), dev(cent, torch.float32), impl=impl)
+    except L.MillionError as e:
+        if impl == L.IMPL_FAST and e.status == L.MILLION_ERR_UNSUPPORTED:
+            pytest.skip("shape not covered by the fast encoder")
+        raise
+    assert np.array_equal(got.cpu().numpy(), golden[f"enc{i}_codes_keops"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("d,Mm,C", [(128, 64, 256), (128, 32, 256), (128, 16, 256), (64, 32, 128), (64, 16, 256)])
+def test_encode_random_bit_exact(M, dtype, d, Mm, C):
+    rng = np.random.default_rng(7)
+    X = torch.from_numpy(rng.standard_normal((2, 3, 301, d), dtype=np.float32)).to(dtype)
+    cent = torch.from_numpy(rng.standard_normal((Mm, C, d // Mm), dtype=np.float32)).to(dtype)
+    ref = O.pq_encode(X.float().numpy(), cent.float().numpy())
+    got = M.pq_encode(X.cuda(), cent.float().cuda())
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_encode_ties_and_wide_codes(M, golden):
+    got = M.pq_encode(dev(golden["tie_X"]), dev(golden["tie_cent"], torch.float32))
+    assert np.array_equal(got.cpu().numpy(), golden["tie_codes"])
+    got = M.pq_encode(dev(golden["wide_X"]), dev(golden["wide_cent"], torch.float32), out_dtype=torch.int32)
+    assert np.array_equal(got.cpu().numpy(), golden["wide_codes"])
+
+
+def test_encode_layouts_strided_transposed_paged(M):
+    rng = np.random.default_rng(3)
+    bs, nh, Lt, d, Mm = 2, 3, 128, 128, 64
+    win = torch.from_numpy(rng.standard_normal((bs, nh, Lt, d), dtype=np.float32)).half().cuda()
+    cent = torch.from_numpy(rng.standard_normal((Mm, 256, 2), dtype=np.float32)).half()
+    ref = O.pq_encode(win[:, :, :64].float().cpu().numpy(), cent.float().numpy())
+    c32 = cent.float().cuda()
+    # strided source slice, append at t0 into a larger cache
+    cache = torch.zeros(bs, nh, 200, Mm, dtype=torch.uint8, device="cuda")
+    M.pq_encode_into(win[:, :, :64], c32, cache, t0=100)
+    assert np.array_equal(cache[:, :, 100:164].cpu().numpy(), ref) and int(cache[:, :, :100].sum()) == 0
+    # transposed store (live PagedPQCache layout)
+    cache_t = torch.zeros(bs, nh, Mm, 256, dtype=torch.uint8, device="cuda")
+    M.pq_encode_into(win[:, :, :64], c32, cache_t, t0=64, layout="transposed")
+    assert np.array_equal(cache_t[:, :, :, 64:128].transpose(2, 3).cpu().numpy(), ref)
+    # paged store: pages handed out chunk-major, b, h
+    pool_ref, table_ref = O.build_page_pool(np.concatenate([ref, ref[:, :, :10]], axis=2), 64)
+    pool = torch.zeros(pool_ref.shape, dtype=torch.uint8, device="cuda")
+    table = dev(table_ref)
+    M.pq_encode_paged(win[:, :, :64], c32, pool, table, t0=0)
+    M.pq_encode_paged(win[:, :, :10], c32, pool, table, t0=64)
+    assert np.array_equal(pool.cpu().numpy(), pool_ref)
+
+
+def test_encode_empty(M):
+    X = torch.zeros(1, 2, 0, 128, dtype=torch.float16, device="cuda")
+    cent = torch.randn(64, 256, 2, device="cuda")
+    assert M.pq_encode(X, cent).shape == (1, 2, 0, 64)
+
+
+# ------------------------------------------------------------------------------------------------ reconstruct
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_decode_golden_exact(M, golden, i):
+    got = M.pq_decode(dev(golden[f"enc{i}_codes_keops"]), dev(golden[f"enc{i}_cent"]))
+    assert got.dtype == torch.float16
+    assert np.array_equal(got.cpu().numpy(), golden[f"enc{i}_decoded"])
+
+
+def test_encode_decode_idempotent(M):
+    """decode(encode(x)) is a fixed point of encode (distinct centroids)."""
+    torch.manual_seed(0)
+    cent = torch.randn(64, 256, 2, device="cuda").half()
+    X = torch.randn(1, 4, 1000, 128, device="cuda").half()
+    codes = M.pq_encode(X, cent.float())
+    again = M.pq_encode(M.pq_decode(codes, cent), cent.float())
+    assert torch.equal(codes, again)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+
+
+def _attn_case(M, g, impl, dtype=torch.float16, v_layout=0, n_splits=0):
+    from million_b200 import _lib as L
+    bs, nh, nh_k, nk, r, d, Mm, C = [int(v) for v in g("shape")]
+    cast = lambda a: dev(a).to(dtype)
+    q, kcent, vcent, kres, vres = cast(g("q")), cast(g("kcent")), cast(g("vcent")), cast(g("kres")), cast(g("vres"))
+    kc, vc = dev(g("kc")), dev(g("vc"))
+    kw = {}
+    if v_layout == L.V_TRANSPOSED:
+        vt = torch.zeros(bs, nh_k, Mm, nk + 37, dtype=torch.uint8, device="cuda")
+        vt[..., :nk] = vc.transpose(2, 3)
+        vc_arg = vt
+    elif v_layout == L.V_PAGED:
+        pool, table = O.build_page_pool(g("vc"), 64)
+        perm = np.random.default_rng(5).permutation(pool.shape[0] + 3)      # scatter the pages
+        pool2 = np.zeros((pool.shape[0] + 3,) + pool.shape[1:], np.uint8)
+        pool2[perm[:pool.shape[0]]] = pool
+        table = perm[table] if table.size else table
+        vc_arg, kw = dev(pool2), dict(v_page_ids=dev(table.astype(np.int64)), page_size=64)
+    else:
+        vc_arg = vc
+    try:
+        out = M.pq_decode_attn(q, kc, vc_arg, kcent, vcent, kres, vres, r, nk=nk, v_layout=v_layout, impl=impl,
+                               n_splits=n_splits, **kw)
+    except L.MillionError as e:
+        if impl == L.IMPL_FAST and e.status == L.MILLION_ERR_UNSUPPORTED:
+            pytest.skip("shape not covered by the fast kernel")
+        raise
+    ref = O.pq_decode_attn(q.float().cpu().numpy(), g("kc"), g("vc"), kcent.float().cpu().numpy(), vcent.float().cpu().numpy(),
+                           kres.float().cpu().numpy(), vres.float().cpu().numpy(), r)
+    return out.float().cpu().numpy(), ref
+
+
+@pytest.mark.parametrize("i", range(4))
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("v_layout", [0, 1, 2])
+def test_attn_golden(M, golden, i, impl, v_layout):
+    g = lambda k: golden[f"att{i}_{k}"]
+    out, ref = _attn_case(M, g, impl, v_layout=v_layout)
+    np.testing.assert_allclose(out, ref, atol=ATOL, rtol=RTOL)
+    # and against the fixture computed by the reference's own functions (fp16 inputs)
+    np.testing.assert_allclose(out, g("out"), atol=ATOL, rtol=RTOL)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attn_dtypes_and_splits(M, golden, impl, dtype):
+    g = lambda k: golden[f"att0_{k}"]
+    for n_splits in (0, 1, 3, 19):
+        out, ref = _attn_case(M, g, impl, dtype=dtype, n_splits=n_splits)
+        np.testing.assert_allclose(out, ref, atol=ATOL if dtype == torch.float16 else 8e-3, rtol=RTOL)
+
+
+def _rand_case(bs, nh, nh_k, nk, r, d=128, Mm=64, C=256, seed=0, dtype=torch.float16):
+    inp = O.make_inputs(bs=bs, nh=nh, nh_k=nh_k, nk=nk, d=d, M=Mm, C=C, Lt=d, seed=seed)
+    t = {k: dev(v) for k, v in inp.items()}
+    for k in ("q", "kcent", "vcent", "kres", "vres"):
+        t[k] = t[k].to(dtype)
+    return inp, t
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("shape", [
+    (1, 8, 8, 4096 - 17, 17),     # BASELINE config 1 (tiny Llama, MHA 8 heads, 4K ctx)
+    (2, 32, 8, 777, 128),         # GQA 4, ragged length, full window
+    (1, 32, 32, 130, 1),          # MHA, r = 1
+    (1, 16, 2, 1, 3),             # GQA 8, a single coded token
+    (3, 4, 4, 0, 9),              # no coded tokens at all
+    (1, 8, 4, 2000, 0),           # empty window (the reference forbids r = 0; we define it)
+])
+def test_attn_random_shapes(M, impl, shape):
+    from million_b200 import _lib as L
+    bs, nh, nh_k, nk, r = shape
+    inp, t = _rand_case(bs, nh, nh_k, nk, r, seed=sum(shape))
+    try:
+        out = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl)
+    except L.MillionError as e:
+        if impl == L.IMPL_FAST and e.status == L.MILLION_ERR_UNSUPPORTED:
+            pytest.skip("shape not covered by the fast kernel")
+        raise
+    if nk + r == 0:
+        assert torch.count_nonzero(out) == 0
+        return
+    ref = O.pq_decode_attn(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], r)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=ATOL, rtol=RTOL)
+
+
+@pytest.mark.parametrize("d,Mm,C", [(128, 32, 256), (128, 16, 256), (64, 32, 256), (64, 16, 128), (128, 64, 128)])
+def test_attn_template_grid_of_the_reference(M, d, Mm, C):
+    """setup.py:10-15 compiles d in {64,128} x M in {16,32,64} x C in {128,256}; all must work (AUTO)."""
+    inp, t = _rand_case(1, 8, 4, 333, 21, d=d, Mm=Mm, C=C, seed=d + Mm + C)
+    out = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 21)
+    ref = O.pq_decode_attn(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], 21)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=ATOL, rtol=RTOL)
+
+
+def test_attn_peaked_distribution(M):
+    """One key dominates (real models have sinks): output ~ that token's value; checks max tracking / rescale."""
+    inp, t = _rand_case(1, 8, 2, 3000, 5, seed=11)
+    q = t["q"].float()
+    q *= 12.0
+    t["q"] = q.half()
+    for impl in (1, 0):
+        out = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 5, impl=impl)
+        ref = O.pq_decode_attn(t["q"].float().cpu().numpy(), inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], 5)
+        np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=4e-3, rtol=RTOL)
+
+
+def test_attn_deterministic_and_counter_reset(M):
+    inp, t = _rand_case(2, 32, 8, 5000, 77, seed=5)
+    outs = [M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 77).clone() for _ in range(5)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+def test_named_bindings_signature(M, golden):
+    """The reference's 10-argument call (pq_utils.py:83-94) through the manufactured name."""
+    from million_b200 import bindings
+    g = lambda k: golden[f"att3_{k}"]
+    bs, nh, nh_k, nk, r, d, Mm, C = [int(v) for v in g("shape")]
+    fn = getattr(bindings, f"flash_decoding_allocated_buffer_f16u8_Ns16Lt{d}d{d}M{Mm}C{C}")
+    po = torch.empty(bs, nh, 17, d, dtype=torch.float16, device="cuda")
+    pl = torch.empty(bs, nh, 17, dtype=torch.float16, device="cuda")
+    out = fn(dev(g("q")), dev(g("kc")), dev(g("vc")), dev(g("kcent")), dev(g("vcent")), dev(g("kres")), dev(g("vres")), r, po, pl)
+    assert out.shape == (bs, nh, 1, d) and out.dtype == torch.float16
+    np.testing.assert_allclose(out.float().cpu().numpy(), g("out"), atol=ATOL, rtol=RTOL)
+    with pytest.raises(TypeError):
+        fn(dev(g("q")).bfloat16(), dev(g("kc")), dev(g("vc")), dev(g("kcent")), dev(g("vcent")), dev(g("kres")), dev(g("vres")), r, po, pl)
+
+
+def test_partial_and_lse_merge_equals_single_call(M):
+    """Split-KV across 'ranks': every rank attends to its token slice (window on the last), partial states are
+    merged with million_lse_merge; must equal the single-call result."""
+    inp, t = _rand_case(1, 32, 8, 4000, 50, seed=9)
+    full = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 50)
+    G = 4
+    parts = torch.empty(G, 32, 130, dtype=torch.float32, device="cuda")
+    per = 4000 // G
+    for g in range(G):
+        kc = t["kc"][:, :, g * per:(g + 1) * per].contiguous()
+        vc = t["vc"][:, :, g * per:(g + 1) * per].contiguous()
+        M.pq_decode_attn(t["q"], kc, vc, t["kcent"], t["vcent"], t["kres"], t["vres"], 50 if g == G - 1 else 0, partial=parts[g])
+    merged = M.lse_merge(parts, 128, torch.float16).view(1, 32, 1, 128)
+    np.testing.assert_allclose(merged.float().cpu().numpy(), full.float().cpu().numpy(), atol=1e-3, rtol=5e-3)
+
+
+def test_full_size_llama31_8b_32k_properties(M):
+    """BASELINE config 2 at full size (bs 1, 32q/8kv heads, 32K ctx): checked against a torch fp32 restatement on the
+    GPU (de-quantise + softmax), and the size-independent property 'all value codes equal -> output is that centroid
+    row mixed only with the window'."""
+    torch.manual_seed(42)
+    bs, nh, nh_k, nk, r, d, Mm, C = 1, 32, 8, 32768 - 128, 128, 128, 64, 256
+    kcent, vcent = torch.randn(Mm, C, 2, device="cuda").half(), torch.randn(Mm, C, 2, device="cuda").half()
+    kc = torch.randint(0, C, (bs, nh_k, nk, Mm), dtype=torch.uint8, device="cuda")
+    vc = torch.randint(0, C, (bs, nh_k, nk, Mm), dtype=torch.uint8, device="cuda")
+    q = torch.randn(bs, nh, 1, d, device="cuda").half()
+    kres, vres = torch.randn(bs, nh_k, 128, d, device="cuda").half(), torch.randn(bs, nh_k, 128, d, device="cuda").half()
+    out = M.pq_decode_attn(q, kc, vc, kcent, vcent, kres, vres, r)
+    ar = torch.arange(Mm, device="cuda")
+    Kh = kcent.float()[ar, kc.long()].reshape(bs, nh_k, nk, d)
+    Vh = vcent.float()[ar, vc.long()].reshape(bs, nh_k, nk, d)
+    K = torch.cat([Kh, kres.float()], 2).repeat_interleave(4, 1)
+    V = torch.cat([Vh, vres.float()], 2).repeat_interleave(4, 1)
+    ref = torch.softmax((q.float() @ K.transpose(-1, -2)) / d ** 0.5, -1) @ V
+    torch.testing.assert_close(out.float(), ref, atol=ATOL, rtol=RTOL)
+    vc.fill_(7)
+    out2 = M.pq_decode_attn(q, kc, vc, kcent, vcent, kres, vres, 0)
+    want = vcent[:, 7, :].reshape(1, 1, 1, d).float().expand(bs, nh, 1, d)
+    torch.testing.assert_close(out2.float(), want, atol=ATOL, rtol=RTOL)
