@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MILLION_ABI_VERSION 1
+#define MILLION_ABI_VERSION 2
 
 typedef void* million_stream_t; /* cudaStream_t */
 
@@ -64,7 +64,7 @@ enum million_v_layout {
 enum million_impl {
     MILLION_IMPL_AUTO = 0,
     MILLION_IMPL_GENERIC = 1, /* plain SIMT kernels, every shape */
-    MILLION_IMPL_FAST = 2     /* decode: shared-memory LUT + mma reduction; encode: tcgen05 distances */
+    MILLION_IMPL_FAST = 2     /* decode: conflict-free shared-memory LUT gathers (attn_fast.cu); encode: tcgen05 distances */
 };
 
 int million_abi_version(void);
@@ -159,9 +159,20 @@ typedef struct million_attn_params {
      * is written here as fp32 (bs, nh, d+2) = [o_unnormalised (d) | running max m | denominator l] and `out`
      * is not touched.  Merge ranks with million_lse_merge. */
     float* partial;
+
+    /* fp16 gather tables made by million_pq_codebook_prepare() from (k_cent, v_cent); required by the FAST
+     * implementation (AUTO falls back to GENERIC when NULL).  Must be re-made whenever the codebooks change. */
+    const void* prepared_codebook;
 } million_attn_params;
 
 #define MILLION_ATTN_PARTIAL_ONLY 1
+
+/* Codebook preparation for the FAST decode-attention kernel: both codebooks as fp16 pairs in the kernel's gather
+ * order (d=128, M=64, C=256 only: returns 0 bytes / MILLION_ERR_UNSUPPORTED otherwise).  One tiny launch; callers
+ * cache the result per codebook (DynamicPQCache.set_cent does). */
+int64_t million_pq_codebook_prepared_bytes(int d, int M, int C);
+int million_pq_codebook_prepare(const void* k_cent, const void* v_cent, int dtype, int d, int M, int C, void* prepared,
+                                million_stream_t stream);
 
 int64_t million_pq_decode_attn_workspace_bytes(int bs, int nh, int nh_k, int d, int max_splits);
 /* the split count AUTO would use (so callers can size the workspace) */

@@ -13,7 +13,7 @@ MILLION_OK, MILLION_ERR_INVALID, MILLION_ERR_UNSUPPORTED, MILLION_ERR_CUDA = 0, 
 V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_FAST = 0, 1, 2
 ATTN_PARTIAL_ONLY = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
 
@@ -35,7 +35,7 @@ class AttnParams(ctypes.Structure):
         ("v_page_ids", c_vp), ("n_pages", c_i32), ("res_len", c_i32),
         ("k_cent", c_vp), ("v_cent", c_vp), ("k_res", c_vp), ("v_res", c_vp),
         ("out", c_vp), ("workspace", c_vp), ("workspace_bytes", c_i64), ("n_splits", c_i32),
-        ("partial", c_vp),
+        ("partial", c_vp), ("prepared_codebook", c_vp),
     ]
 
 
@@ -50,6 +50,8 @@ SIGNATURES = {
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "million_pq_decode": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, ctypes.c_int, c_i64,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "million_pq_codebook_prepared_bytes": (c_i64, [ctypes.c_int] * 3),
+    "million_pq_codebook_prepare": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "million_pq_decode_attn_workspace_bytes": (c_i64, [ctypes.c_int] * 5),
     "million_pq_decode_attn_default_splits": (ctypes.c_int, [ctypes.c_int] * 3),
     "million_pq_decode_attn": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),

@@ -1,0 +1,531 @@
+// attn_fast.cu — the B200 decode-attention kernel for the common shape d=128, M=64 (d_m=2), C=256,
+// G = nh/nh_k in {1,2,4} (larger groups run as several 4-head sub-groups).
+//
+// What bounds this op on B200 is not HBM alone but the shared-memory gather rate (128 B/clk/SM): every coded
+// token needs 64 K-LUT lookups and 64 V-codebook lookups.  tools/microbench*.cu measured on B200: LDS.64
+// conflict-free 2.09 clk/warp-instr, random banks 4.9; LDS.32 1.13; and mma.sync *serialises* with LDS
+// (1 mma + 8 LDS.64 costs the sum), so tensor-core reductions are out.  Hence:
+//   * QK: thread-per-token; lane l visits the 16 code words of its token in an order rotated by
+//     rot(l) = (l%16 + l/16) % 16, so at every step the 16 lanes of a half-warp hit 16 different
+//     sub-space columns = 16 different bank pairs -> every LUT gather is conflict free, and no cross-lane
+//     reduction is ever needed.  The gather address is formed by ONE PRMT: (code << 8) | column_offset.
+//   * LUT entries hold all G heads of the KV group packed as fp16 (8 B for G=4) -> one gather serves 4 heads;
+//     partial sums run in packed half2 over 16 entries, then flush to fp32.
+//   * PV: a half-warp per token, lane owns 4 sub-spaces; V-codebook gathers are conflict free the same way;
+//     p is broadcast through a 16-byte shared slot; products accumulate in half2 per 32-token tile, fp32 across.
+//   * each warp streams its own 32-token code tiles with a private cp.async double buffer: no block barrier in
+//     the main loop; online softmax state is per warp and merged once at the end.
+//   * the fp16 window and the cross-CTA merge are fused (last split CTA / last-arrival ticket).
+// Replaces Interface.cu:49-118 + Kernel.cuh:11-166, 1038-1209, 1211-1270 of the reference.
+#include "attn_common.cuh"
+
+namespace million {
+
+namespace fast {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTile = 32;                       // tokens per warp tile
+constexpr int kRowBytes = 64;                   // M = 64 one-byte codes
+constexpr int kStageBytes = 2 * kTile * kRowBytes;   // K tile + V tile
+constexpr int kVtabBytes = 64 * 1024;
+constexpr float kRescaleMargin = 6.f;           // log2 units: p <= 64 before a rescale is forced
+
+template <int G> struct LutCfg;
+template <> struct LutCfg<4> { static constexpr int bytes = 128 * 1024; };
+template <> struct LutCfg<2> { static constexpr int bytes = 64 * 1024; };
+template <> struct LutCfg<1> { static constexpr int bytes = 64 * 1024; };
+
+// column of sub-space m inside a 64-entry table row (both K tables and the V table)
+__host__ __device__ __forceinline__ constexpr int col_of(int m) {
+    const int W = m >> 2, b = m & 3;
+    return (b >> 1) * 32 + (b & 1) * 16 + W;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// plain shared-memory loads through the generic pointer of the dynamic smem block: the compiler is free to batch them
+// (asm volatile loads would be kept in program order and serialise on the 30-cycle LDS latency)
+__device__ __forceinline__ uint32_t lds32(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint32_t*>(base + off); }
+__device__ __forceinline__ uint2 lds64(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint2*>(base + off); }
+__device__ __forceinline__ uint4 lds128(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint4*>(base + off); }
+// acc_lo += fp16(packed.lo), acc_hi += fp16(packed.hi) in fp32: Blackwell FHADD (PTX add.rn.f32.f16), one op each
+__device__ __forceinline__ void fhadd2(float& acc_lo, float& acc_hi, uint32_t packed) {
+    const unsigned short lo = (unsigned short)(packed & 0xffffu), hi = (unsigned short)(packed >> 16);
+    asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc_lo) : "h"(lo));
+    asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc_hi) : "h"(hi));
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+}  // namespace fast
+
+// ------------------------------------------------------------------------------------------------
+// Codebook preparation (once per codebook): fp16 tables in the column order the kernel gathers with.
+//   prepared[0      .. 64 KB) : kT[c][col(m)] = half2(Kcent[m][c][0], Kcent[m][c][1])
+//   prepared[64 KB .. 128 KB) : vT[c][col(m)] = half2(Vcent[m][c][0], Vcent[m][c][1])
+template <typename T>
+__global__ void codebook_prepare_kernel(const T* __restrict__ kcent, const T* __restrict__ vcent, uint32_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 2 * 64 * 256
+    if (idx >= 2 * 64 * 256) return;
+    const int which = idx / (64 * 256), rem = idx % (64 * 256);
+    const int m = rem / 256, c = rem % 256;
+    const T* src = (which ? vcent : kcent) + ((int64_t)m * 256 + c) * 2;
+    const __half2 v = __floats2half2_rn(io<T>::to_f(src[0]), io<T>::to_f(src[1]));
+    out[which * 64 * 256 + c * 64 + fast::col_of(m)] = fast::as_u32(v);
+}
+
+int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, void* out, cudaStream_t stream) {
+    dim3 grid(2 * 64 * 256 / 256), block(256);
+    if (io_dtype == MILLION_F16) codebook_prepare_kernel<__half><<<grid, block, 0, stream>>>((const __half*)kcent, (const __half*)vcent, (uint32_t*)out);
+    else if (io_dtype == MILLION_BF16) codebook_prepare_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)kcent, (const __nv_bfloat16*)vcent, (uint32_t*)out);
+    else codebook_prepare_kernel<float><<<grid, block, 0, stream>>>((const float*)kcent, (const float*)vcent, (uint32_t*)out);
+    MILLION_CUDA_OK(cudaGetLastError());
+    return MILLION_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace fast {
+
+// Per-warp online-softmax state (uniform across the lanes of the warp) and accumulators.
+template <int G>
+struct WarpState {
+    float m[G];          // running max, log2 units (scaled logits)
+    float l[G];          // per-LANE partial denominator (summed across lanes at the end)
+    float o[4][G][2];    // per-lane fp32 output accumulators: slot b -> sub-space 4*l' + ((b + hw) & 3), 2 dims
+};
+
+template <int G>
+__device__ __forceinline__ void state_init(WarpState<G>& st) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) { st.m[g] = -INFINITY; st.l[g] = 0.f; }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) { st.o[b][g][0] = 0.f; st.o[b][g][1] = 0.f; }
+}
+
+// Raise the running max to at least new_m (per head) and rescale everything accumulated so far.
+template <int G>
+__device__ __forceinline__ void state_rescale(WarpState<G>& st, const float (&new_m)[G]) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (new_m[g] > st.m[g]) {
+            const float alpha = exp2_safe(st.m[g], new_m[g]);
+            st.l[g] *= alpha;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { st.o[b][g][0] *= alpha; st.o[b][g][1] *= alpha; }
+            st.m[g] = new_m[g];
+        }
+    }
+}
+
+}  // namespace fast
+
+template <typename T, int G>
+__global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
+    using namespace fast;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* lut_p = smem;
+    unsigned char* vtab_p = smem + LutCfg<G>::bytes;
+    unsigned char* stage_p = vtab_p + kVtabBytes;                       // kWarps * 2 * kStageBytes
+    unsigned char* pbuf_p = stage_p + kWarps * 2 * kStageBytes;         // kWarps * kTile * 16
+    // after the main loop the stage buffers are dead: reuse them for the cross-warp merge and the window
+    float* qs = reinterpret_cast<float*>(stage_p);                      // G * 128 floats (window)
+    float* xch = qs + 4 * 128;                                          // kWarps * (G*128 + 2*G) floats
+    __shared__ int flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int split = blockIdx.x;
+    // blockIdx.y enumerates (kv head, 4-head sub-group) when the GQA group is larger than 4
+    const int hk = blockIdx.y / gsub, sub = blockIdx.y % gsub, b = blockIdx.z;
+    const int Gfull = a.nh / a.nh_k;
+    const int h0 = hk * Gfull + sub * G;                                // first query head of this CTA
+    const int hb = b * a.nh_k + hk;
+    const int n_parts = a.n_splits + 1;
+
+    int t0, t1;
+    split_range(a, split, t0, t1);
+    const bool has_codes = t1 > t0;
+
+    const uint32_t lut_s = smem_u32(lut_p), vtab_s = smem_u32(vtab_p);
+
+    // ---------------------------------------------------------------- prologue: V table + K LUT
+    if (has_codes) {
+        // The K gather table kT (64 KB, L2 resident) streams through the stage area in four 16 KB chunks (cp.async double
+        // buffer); the V table (already in gather order) is copied straight to its place in the background.
+        const uint32_t stage0 = smem_u32(stage_p);
+        auto load_chunk = [&](int ch) {
+            const char* src = reinterpret_cast<const char*>(prepared) + ch * 16384;
+            const uint32_t dst = stage0 + (ch & 1) * 16384;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp_async16(dst + (tid + i * kThreads) * 16, src + (tid + i * kThreads) * 16, 16);
+            cp_async_commit();
+        };
+        load_chunk(0);
+        {
+            const uint4* vsrc = reinterpret_cast<const uint4*>(prepared + 64 * 256);
+            for (int i = tid; i < kVtabBytes / 16; i += kThreads) cp_async16(vtab_s + i * 16, vsrc + i, 16);
+            cp_async_commit();
+        }
+        load_chunk(1);
+        // K LUT: thread owns column `col` (= one sub-space) and walks the codes.  LUT[c][col] = <q_h[m], Kcent[m][c]> for the
+        // G heads of the group: fp32 products of fp16 operands, rounded once to fp16 (G=1 keeps fp32 entries).
+        const int col = tid & 63;
+        const int bb = ((col >> 5) << 1) | ((col >> 4) & 1), W = col & 15, m = 4 * W + bb;
+        float q0[G], q1[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const T* q = reinterpret_cast<const T*>(a.q) + (int64_t)(b * a.nh + h0 + g) * 128;
+            q0[g] = io<T>::to_f(q[2 * m]);
+            q1[g] = io<T>::to_f(q[2 * m + 1]);
+        }
+        for (int ch = 0; ch < 4; ++ch) {
+            if (ch == 0) cp_async_wait<2>();        // pending: [chunk0, vtab, chunk1] -> chunk0 landed
+            else if (ch < 3) cp_async_wait<1>();    // chunk ch landed (and the V table)
+            else cp_async_wait<0>();
+            __syncthreads();
+            const unsigned char* src = stage_p + (ch & 1) * 16384;
+#pragma unroll 4
+            for (int cl = tid >> 6; cl < 64; cl += kThreads / 64) {
+                const int c = ch * 64 + cl;
+                const __half2 cv = as_h2(*reinterpret_cast<const uint32_t*>(src + (cl * 64 + col) * 4));
+                const float c0 = __low2float(cv), c1 = __high2float(cv);
+                if constexpr (G == 4) {
+                    const __half2 e01 = __floats2half2_rn(fmaf(c1, q1[0], c0 * q0[0]), fmaf(c1, q1[1], c0 * q0[1]));
+                    const __half2 e23 = __floats2half2_rn(fmaf(c1, q1[2], c0 * q0[2]), fmaf(c1, q1[3], c0 * q0[3]));
+                    // address(m, c) = (b>>1)*64K + c*256 + ((b&1)*16 + W)*8
+                    *reinterpret_cast<uint2*>(lut_p + (bb >> 1) * 65536 + c * 256 + ((bb & 1) * 16 + W) * 8) = make_uint2(as_u32(e01), as_u32(e23));
+                } else if constexpr (G == 2) {
+                    const __half2 e01 = __floats2half2_rn(fmaf(c1, q1[0], c0 * q0[0]), fmaf(c1, q1[1], c0 * q0[1]));
+                    *reinterpret_cast<uint32_t*>(lut_p + c * 256 + col * 4) = as_u32(e01);
+                } else {
+                    *reinterpret_cast<float*>(lut_p + c * 256 + col * 4) = fmaf(c1, q1[0], c0 * q0[0]);
+                }
+            }
+            __syncthreads();
+            if (ch + 2 < 4) load_chunk(ch + 2);
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- main loop over this warp's tiles
+    WarpState<G> st;
+    state_init(st);
+
+    if (has_codes) {
+        const int lq = lane & 15, hw = lane >> 4;
+        const int rot = (lq + hw) & 15;
+        const uint32_t stage_s = smem_u32(stage_p) + warp * 2 * kStageBytes;
+        unsigned char* pbuf_w = pbuf_p + warp * kTile * 16;
+        const uint8_t* kbase = a.k_codes + hb * a.k_head_stride;
+        const uint8_t* vbase = a.v_codes + hb * a.v_head_stride;
+
+        // per-lane gather constants
+        uint32_t koff[16];   // QK: byte0 = column offset for even b, byte1 = for odd b, bytes 2,3 = 0
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+            const int Wl = (w + rot) & 15;
+            if constexpr (G == 4) koff[w] = (uint32_t)(Wl * 8) | ((uint32_t)(Wl * 8 + 128) << 8);
+            else koff[w] = (uint32_t)(Wl * 4) | ((uint32_t)(Wl * 4 + 64) << 8);   // + (bb>>1)*128 comes from the immediate
+        }
+        // PV: slot s -> byte bb = (s + hw) & 3 of the lane's V code word; column offset col_of(4*lq + bb) * 4
+        uint32_t voff01, voff23, vsel[4];
+        {
+            uint32_t o[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int bb = (s + hw) & 3;
+                o[s] = (uint32_t)(col_of(4 * lq + bb) * 4);
+                // result = [off (from voff, byte 4 + (s&1)), code (byte bb of the word), 0, 0]
+                vsel[s] = (uint32_t)(4 + (s & 1)) | ((uint32_t)bb << 4) | (6u << 8) | (6u << 12);
+            }
+            voff01 = o[0] | (o[1] << 8);
+            voff23 = o[2] | (o[3] << 8);
+        }
+
+        const int n_tiles = (t1 - t0 + kTile - 1) / kTile;
+        auto issue = [&](int tile, int stg) {
+            // 32 tokens * 64 B for K and for V: 128 chunks of 16 B each -> 4 + 4 per lane
+            const int tok0 = t0 + tile * kTile;
+            const uint32_t dst = stage_s + stg * kStageBytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int chunk = lane + i * 32;            // 0..127
+                const int tok = tok0 + (chunk >> 2);
+                const int ok = (tile < n_tiles && tok < t1) ? 16 : 0;
+                const int64_t off = (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16;
+                cp_async16(dst + chunk * 16, kbase + off, ok);
+                cp_async16(dst + kTile * kRowBytes + chunk * 16, vbase + off, ok);
+            }
+            cp_async_commit();
+        };
+
+        issue(warp, 0);
+        int stg = 0;
+        bool first = true;
+        for (int tile = warp; tile < n_tiles; tile += kWarps, stg ^= 1) {
+            issue(tile + kWarps, stg ^ 1);
+            cp_async_wait<1>();
+            __syncwarp();
+            const unsigned char* ksp = stage_p + (warp * 2 + stg) * kStageBytes;
+            const unsigned char* vsp = ksp + kTile * kRowBytes;
+            const int tok = t0 + tile * kTile + lane;
+            const bool valid = tok < t1;
+
+            // ------------------------------------------------ QK: 64 conflict-free LUT gathers for my token
+            float s[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) s[g] = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                // my token's code word number (w + rot) % 16
+                const uint32_t word = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));
+#pragma unroll
+                for (int bq = 0; bq < 4; ++bq) {
+                    if constexpr (G == 4) {
+                        const uint32_t sel = (uint32_t)(4 + (bq & 1)) | ((uint32_t)bq << 4) | (6u << 8) | (6u << 12);
+                        const uint32_t ad = __byte_perm(word, koff[w], sel);          // (code << 8) | column offset
+                        const uint2 e = lds64(lut_p + (bq >> 1) * 65536, ad);
+                        fhadd2(s[0], s[1], e.x);
+                        fhadd2(s[2], s[3], e.y);
+                    } else {
+                        // the two half-warps use different bytes in the same step so that all 32 lanes hit 32 banks
+                        const int bb_1 = (bq + 1) & 3;
+                        const uint32_t sel0 = (uint32_t)(4 + (bq & 1)) | ((uint32_t)bq << 4) | (6u << 8) | (6u << 12);
+                        const uint32_t sel1 = (uint32_t)(4 + (bb_1 & 1)) | ((uint32_t)bb_1 << 4) | (6u << 8) | (6u << 12);
+                        const uint32_t ad = __byte_perm(word, koff[w], hw ? sel1 : sel0);
+                        const uint32_t imm = (uint32_t)(((hw ? bb_1 : bq) >> 1) * 128);
+                        const uint32_t e = lds32(lut_p + imm, ad);
+                        if constexpr (G == 2) fhadd2(s[0], s[1], e);
+                        else s[0] += __uint_as_float(e);
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) s[g] = valid ? s[g] * a.scale_log2 : -INFINITY;
+
+            // ------------------------------------------------ online softmax (lazy max: rescale only when needed)
+            bool need = first;
+#pragma unroll
+            for (int g = 0; g < G; ++g) need = need || (s[g] > st.m[g] + kRescaleMargin);
+            if (__any_sync(0xffffffffu, need)) {
+                float nm[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) nm[g] = fmaxf(st.m[g], warp_max(s[g]));
+                state_rescale<G>(st, nm);
+                first = false;
+            }
+            float p[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                p[g] = exp2_safe(s[g], st.m[g]);
+                st.l[g] += p[g];
+            }
+            // p for the PV phase: half2(p_g, p_g), 16 bytes per token
+            {
+                uint4 pk = make_uint4(0, 0, 0, 0);
+                pk.x = as_u32(__float2half2_rn(p[0]));
+                if constexpr (G >= 2) pk.y = as_u32(__float2half2_rn(p[1]));
+                if constexpr (G == 4) { pk.z = as_u32(__float2half2_rn(p[2])); pk.w = as_u32(__float2half2_rn(p[3])); }
+                *reinterpret_cast<uint4*>(pbuf_w + lane * 16) = pk;
+            }
+            __syncwarp();
+
+            // ------------------------------------------------ PV: half-warp per token, lane owns 4 sub-spaces
+            __half2 acc[4][G];
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[sl][g] = __float2half2_rn(0.f);
+#pragma unroll 4
+            for (int jp = 0; jp < kTile / 2; ++jp) {
+                const int j = 2 * jp + hw;
+                const uint32_t word = lds32(vsp, j * kRowBytes + lq * 4);
+                const uint4 pk = lds128(pbuf_w, j * 16);
+                const uint32_t pr[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    const uint32_t ad = __byte_perm(word, sl < 2 ? voff01 : voff23, vsel[sl]);
+                    const __half2 v = as_h2(lds32(vtab_p, ad));
+#pragma unroll
+                    for (int g = 0; g < G; ++g) acc[sl][g] = __hfma2(as_h2(pr[g]), v, acc[sl][g]);
+                }
+            }
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float2 f = __half22float2(acc[sl][g]);
+                    st.o[sl][g][0] += f.x;
+                    st.o[sl][g][1] += f.y;
+                }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+    }
+
+    __syncthreads();   // every warp is done with its stage buffers (aliased below)
+    // ---------------------------------------------------------------- combine the warps of this CTA -> partial
+    // lane layout: slot sl of lane (hw, lq) holds sub-space 4*lq + ((sl + hw) & 3).  First fold hw=1 into hw=0.
+    {
+        const int lq = lane & 15, hw = lane >> 4;
+#pragma unroll
+        for (int g = 0; g < G; ++g) st.l[g] = warp_sum(st.l[g]);
+        float o2[4][G][2];   // indexed by byte bb (sub-space 4*lq + bb) after the fold, valid in lanes hw = 0
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    // partner (hw=1) slot (sl - 1) & 3 holds the same sub-space as my (hw=0) slot sl
+                    const float mine = st.o[sl][g][k];
+                    const float theirs = __shfl_xor_sync(0xffffffffu, st.o[(sl + 3) & 3][g][k], 16);
+                    o2[sl][g][k] = mine + theirs;
+                }
+        float* wx = xch + warp * (G * 128 + 2 * G);
+        if (hw == 0) {
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int m = 4 * lq + sl;
+                    wx[g * 128 + 2 * m] = o2[sl][g][0];
+                    wx[g * 128 + 2 * m + 1] = o2[sl][g][1];
+                }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) { wx[G * 128 + g] = st.m[g]; wx[G * 128 + G + g] = st.l[g]; }
+        }
+    }
+    __syncthreads();
+    {
+        // thread t -> dim t (128 threads = 128 dims), all G heads
+        for (int g = 0; g < G; ++g) {
+            float mstar = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) mstar = fmaxf(mstar, xch[w * (G * 128 + 2 * G) + G * 128 + g]);
+            float o = 0.f, l = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const float* wx = xch + w * (G * 128 + 2 * G);
+                const float sc = exp2_safe(wx[G * 128 + g], mstar);
+                o += wx[g * 128 + tid] * sc;
+                l += wx[G * 128 + G + g] * sc;
+            }
+            float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * n_parts + split) * 130;
+            part[tid] = o;
+            if (tid == 0) { part[128] = mstar; part[129] = l; }
+        }
+    }
+
+    // ---------------------------------------------------------------- fp16 window (exact attention), part index n_splits
+    if (split == a.n_splits - 1) {
+        __syncthreads();
+        float* S = xch;                 // G * 128 scores / probabilities (xch is free again)
+        const int r = a.r;
+        for (int i = tid; i < G * 128; i += kThreads)
+            qs[i] = io<T>::to_f(reinterpret_cast<const T*>(a.q)[(int64_t)(b * a.nh + h0) * 128 + i]) * a.scale_log2;
+        __syncthreads();
+        float sc[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) sc[g] = -INFINITY;
+        if (tid < r) {
+            const uint4* kr = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_res) + ((int64_t)hb * a.res_len + tid) * 128);
+#pragma unroll
+            for (int g = 0; g < G; ++g) sc[g] = 0.f;
+#pragma unroll 4
+            for (int c = 0; c < 16; ++c) {
+                const uint4 v = __ldg(kr + c);
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 kf = io<T>::to_f2(wv[e]);
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        sc[g] = fmaf(kf.y, qs[g * 128 + c * 8 + e * 2 + 1], fmaf(kf.x, qs[g * 128 + c * 8 + e * 2], sc[g]));
+                }
+            }
+        }
+        __shared__ float red[33];
+        float wm[G], wl[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            wm[g] = block_reduce<true>(sc[g], red);
+            const float p = (tid < r) ? exp2_safe(sc[g], wm[g]) : 0.f;
+            wl[g] = block_reduce<false>(p, red);
+            S[g * 128 + tid] = p;
+        }
+        __syncthreads();
+        float o[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) o[g] = 0.f;
+        const T* vr = reinterpret_cast<const T*>(a.v_res) + (int64_t)hb * a.res_len * 128 + tid;
+        for (int j = 0; j < r; ++j) {
+            const float v = io<T>::to_f(vr[(int64_t)j * 128]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) o[g] = fmaf(S[g * 128 + j], v, o[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * n_parts + a.n_splits) * 130;
+            part[tid] = o[g];
+            if (tid == 0) { part[128] = wm[g]; part[129] = wl[g]; }
+        }
+    }
+
+    // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
+    if (last_cta_of_group(a.counters, hb, a.n_splits * gsub, &flag)) merge_group<T>(a, b, hk);
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+template <typename T, int G>
+static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
+    using namespace fast;
+    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * 2 * kStageBytes + kWarps * kTile * 16;
+    static_assert(kWarps * 2 * kStageBytes >= (4 * 128 + kWarps * (4 * 128 + 8)) * sizeof(float), "stage area too small for the epilogue");
+    static bool configured = false;
+    if (!configured) {
+        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
+    attn_fast_kernel<T, G><<<grid, block, smem, stream>>>(a, prepared, gsub);
+    MILLION_CUDA_OK(cudaGetLastError());
+    return MILLION_OK;
+}
+
+int launch_attn_fast(const AttnArgs& a, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only) {
+    const int Gfull = a.nh / a.nh_k;
+    if (a.d != 128 || a.M != 64 || a.C != 256) MILLION_UNSUPPORTED("fast decode attention needs d=128, M=64, C=256");
+    if (!(Gfull == 1 || Gfull == 2 || Gfull % 4 == 0)) MILLION_UNSUPPORTED("fast decode attention needs nh/nh_k in {1,2,4k}");
+    if (a.v_layout != MILLION_V_ROWMAJOR) MILLION_UNSUPPORTED("fast decode attention: V layout %d not supported yet", a.v_layout);
+    if (!prepared) MILLION_UNSUPPORTED("fast decode attention needs a prepared codebook (million_pq_codebook_prepare)");
+    if (a.nk > 0 && (((uintptr_t)a.k_codes | (uintptr_t)a.v_codes | (uintptr_t)a.k_head_stride | (uintptr_t)a.v_head_stride) & 15))
+        MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");
+    if (a.r > 128 || ((uintptr_t)a.k_res & 15)) MILLION_UNSUPPORTED("fast decode attention needs r <= 128 and aligned window");
+    if (probe_only) return MILLION_OK;
+    const int G = Gfull >= 4 ? 4 : Gfull, gsub = Gfull >= 4 ? Gfull / 4 : 1;
+    const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
+#define MILLION_FAST_CASE(TT, GG) return launch_fast_t<TT, GG>(a, prep, gsub, stream)
+    if (io_dtype == MILLION_F16) {
+        if (G == 4) MILLION_FAST_CASE(__half, 4);
+        if (G == 2) MILLION_FAST_CASE(__half, 2);
+        MILLION_FAST_CASE(__half, 1);
+    } else {
+        if (G == 4) MILLION_FAST_CASE(__nv_bfloat16, 4);
+        if (G == 2) MILLION_FAST_CASE(__nv_bfloat16, 2);
+        MILLION_FAST_CASE(__nv_bfloat16, 1);
+    }
+#undef MILLION_FAST_CASE
+}
+
+}  // namespace million

@@ -34,7 +34,8 @@ int sm_count() {
 
 struct CodeDst;
 int launch_attn_generic(const AttnArgs& a, int io_dtype, cudaStream_t stream);
-int launch_attn_fast(const AttnArgs& a, int io_dtype, cudaStream_t stream, bool probe_only);
+int launch_attn_fast(const AttnArgs& a, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only);
+int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, void* out, cudaStream_t stream);
 int launch_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, cudaStream_t stream);
 int launch_reconstruct(const void* codes, int code_bytes, int64_t chs, int64_t cts, int64_t cms, const void* cent, void* out,
                        int dtype, int64_t ohs, int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream);
@@ -104,6 +105,16 @@ int million_pq_decode(const void* codes, int code_bytes, int64_t chs, int64_t ct
                               (cudaStream_t)stream);
 }
 
+int64_t million_pq_codebook_prepared_bytes(int d, int M, int C) { return (d == 128 && M == 64 && C == 256) ? 2 * 64 * 256 * 4 : 0; }
+
+int million_pq_codebook_prepare(const void* k_cent, const void* v_cent, int dtype, int d, int M, int C, void* prepared,
+                                million_stream_t stream) {
+    MILLION_REQUIRE(k_cent && v_cent && prepared, "codebook_prepare: null pointer");
+    MILLION_REQUIRE(dtype >= MILLION_F16 && dtype <= MILLION_F32, "codebook_prepare: bad dtype");
+    if (million_pq_codebook_prepared_bytes(d, M, C) == 0) MILLION_UNSUPPORTED("codebook_prepare: only d=128, M=64, C=256");
+    return launch_codebook_prepare(k_cent, v_cent, dtype, prepared, (cudaStream_t)stream);
+}
+
 int million_pq_decode_attn_default_splits(int bs, int nh_k, int nk) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int groups = bs * nh_k > 0 ? bs * nh_k : 1;
@@ -165,8 +176,9 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
 
     cudaStream_t st = (cudaStream_t)stream;
     if (p->impl == MILLION_IMPL_GENERIC) return launch_attn_generic(a, p->io_dtype, st);
-    if (p->impl == MILLION_IMPL_FAST) return launch_attn_fast(a, p->io_dtype, st, false);
-    if (launch_attn_fast(a, p->io_dtype, st, true) == MILLION_OK) return launch_attn_fast(a, p->io_dtype, st, false);
+    if (p->impl == MILLION_IMPL_FAST) return launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, false);
+    if (launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, true) == MILLION_OK)
+        return launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, false);
     return launch_attn_generic(a, p->io_dtype, st);
 }
 

@@ -3,7 +3,6 @@
 #include "codec.cuh"
 namespace million {
 
-int launch_attn_fast(const AttnArgs&, int, cudaStream_t, bool) { set_error("fast decode attention not built"); return MILLION_ERR_UNSUPPORTED; }
 int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float* cent, void* codes, int code_bytes, int64_t chs,
                     int64_t cts, int64_t cms, int64_t t0, const int64_t* page_ids, int64_t pihs, int page_size, int n_heads,
                     int n_tokens, int d, int M, int C, int impl, cudaStream_t stream) {

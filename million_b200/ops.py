@@ -124,8 +124,31 @@ def default_splits(bs, nh_k, nk):
     return L.lib().million_pq_decode_attn_default_splits(bs, nh_k, nk)
 
 
+_prepared = {}
+
+
+def prepare_codebooks(k_cent, v_cent):
+    """fp16 gather tables for the fast kernel (None when the shape is not covered).  Cached per codebook tensor and
+    torch version counter, so in-place edits of the centroids are noticed."""
+    M, C, dm = k_cent.shape
+    nbytes = L.lib().million_pq_codebook_prepared_bytes(M * dm, M, C)
+    if nbytes == 0:
+        return None
+    key = (k_cent.data_ptr(), v_cent.data_ptr(), k_cent._version, v_cent._version, k_cent.dtype, k_cent.device)
+    hit = _prepared.get(key)
+    if hit is None:
+        if len(_prepared) > 64:
+            _prepared.clear()
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=k_cent.device)
+        L.check(L.lib().million_pq_codebook_prepare(_ptr(k_cent), _ptr(v_cent), _dt(k_cent), M * dm, M, C, _ptr(buf), _stream(k_cent)))
+        hit = (buf, k_cent, v_cent)          # keep the sources alive so data_ptr keys cannot be recycled
+        _prepared[key] = hit
+    return hit[0]
+
+
 def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=None, v_layout=L.V_ROWMAJOR,
-                   v_page_ids=None, page_size=0, out=None, partial=None, n_splits=0, impl=L.IMPL_AUTO, workspace=None):
+                   v_page_ids=None, page_size=0, out=None, partial=None, n_splits=0, impl=L.IMPL_AUTO, workspace=None,
+                   prepared=None):
     """One decode-attention call (include/million_b200.h: million_pq_decode_attn).
 
     q (bs, nh, 1, d) | (bs, nh, d); k_codes (bs, nh_k, >=nk, M) uint8 (head stride taken from the tensor);
@@ -162,6 +185,11 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
             p.v_page_ids, p.n_pages, p.page_size = v_page_ids.data_ptr(), v_page_ids.shape[2], page_size or v_codes.shape[2]
     p.v_layout = v_layout
     p.k_cent, p.v_cent = k_cent.data_ptr(), v_cent.data_ptr()
+    if impl != L.IMPL_GENERIC:
+        if prepared is None:
+            prepared = prepare_codebooks(k_cent, v_cent)
+        if prepared is not None:
+            p.prepared_codebook = prepared.data_ptr()
     p.res_len = k_res.shape[2] if k_res is not None else 0
     if r:
         assert k_res.dtype == q.dtype and v_res.dtype == q.dtype
