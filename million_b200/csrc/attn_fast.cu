@@ -23,11 +23,11 @@ namespace million {
 
 namespace fast {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTile = 32;                       // tokens per warp tile
 constexpr int kRowBytes = 64;                   // M = 64 one-byte codes
-constexpr int kStageBytes = 2 * kTile * kRowBytes;   // K tile + V tile
+constexpr int kStageBytes = 2 * kTile * kRowBytes;   // one K tile + one V tile per warp
 constexpr int kVtabBytes = 64 * 1024;
 constexpr float kRescaleMargin = 6.f;           // log2 units: p <= 64 before a rescale is forced
 
@@ -98,7 +98,7 @@ template <int G>
 struct WarpState {
     float m[G];          // running max, log2 units (scaled logits)
     float l[G];          // per-LANE partial denominator (summed across lanes at the end)
-    float o[4][G][2];    // per-lane fp32 output accumulators: slot b -> sub-space 4*l' + ((b + hw) & 3), 2 dims
+    float o[4][G][2];    // per-lane fp32 output accumulators: slot s -> sub-space 4*l' + ((s + hw) & 3), 2 dims
 };
 
 template <int G>
@@ -111,19 +111,21 @@ __device__ __forceinline__ void state_init(WarpState<G>& st) {
         for (int g = 0; g < G; ++g) { st.o[b][g][0] = 0.f; st.o[b][g][1] = 0.f; }
 }
 
-// Raise the running max to at least new_m (per head) and rescale everything accumulated so far.
-template <int G>
-__device__ __forceinline__ void state_rescale(WarpState<G>& st, const float (&new_m)[G]) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        if (new_m[g] > st.m[g]) {
-            const float alpha = exp2_safe(st.m[g], new_m[g]);
-            st.l[g] *= alpha;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) { st.o[b][g][0] *= alpha; st.o[b][g][1] *= alpha; }
-            st.m[g] = new_m[g];
-        }
-    }
+// Table gathers with an absolute shared-window address: the PRMT result (code << 8 | column offset) is the register part,
+// the table base is an immediate, so a gather is exactly PRMT + LDS.  Not volatile: the tables are read-only in the main
+// loop and the compiler may schedule these loads freely.  kSmemBase is checked at kernel entry.
+constexpr uint32_t kSmemBase = 0x400;   // dynamic shared memory starts after the 1 KB the driver reserves per CTA (no static smem)
+template <uint32_t IMM>
+__device__ __forceinline__ uint2 gather64(uint32_t r) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(r), "n"(IMM));
+    return v;
+}
+template <uint32_t IMM>
+__device__ __forceinline__ uint32_t gather32(uint32_t r) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(r), "n"(IMM));
+    return v;
 }
 
 }  // namespace fast
@@ -132,16 +134,23 @@ template <typename T, int G>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
     using namespace fast;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* lut_p = smem;
-    unsigned char* vtab_p = smem + LutCfg<G>::bytes;
-    unsigned char* stage_p = vtab_p + kVtabBytes;                       // kWarps * 2 * kStageBytes
-    unsigned char* pbuf_p = stage_p + kWarps * 2 * kStageBytes;         // kWarps * kTile * 16
+    constexpr uint32_t kLutOff = 0, kVtabOff = LutCfg<G>::bytes, kStageOff = kVtabOff + kVtabBytes;
+    constexpr uint32_t kPbufOff = kStageOff + kWarps * kStageBytes, kMiscOff = kPbufOff + kWarps * kTile * 8;
+    unsigned char* lut_p = smem + kLutOff;
+    unsigned char* stage_p = smem + kStageOff;                           // kWarps * (K tile + V tile)
+    unsigned char* pbuf_p = smem + kPbufOff;                             // kWarps * kTile * 8 bytes (4 halves per token)
+    int* flag = reinterpret_cast<int*>(smem + kMiscOff);
+    float* red = reinterpret_cast<float*>(smem + kMiscOff + 16);         // 33 floats
     // after the main loop the stage buffers are dead: reuse them for the cross-warp merge and the window
-    float* qs = reinterpret_cast<float*>(stage_p);                      // G * 128 floats (window)
-    float* xch = qs + 4 * 128;                                          // kWarps * (G*128 + 2*G) floats
-    __shared__ int flag;
+    float* qs = reinterpret_cast<float*>(stage_p);                       // 4 * 128 floats (window)
+    float* xch = qs + 4 * 128;                                           // kWarps * (G*128 + 2*G) floats
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (smem_u32(smem) != kSmemBase) {
+        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+            printf("million_b200: dynamic shared memory starts at 0x%x, expected 0x%x\n", smem_u32(smem), kSmemBase);
+        __trap();
+    }
     const int split = blockIdx.x;
     // blockIdx.y enumerates (kv head, 4-head sub-group) when the GQA group is larger than 4
     const int hk = blockIdx.y / gsub, sub = blockIdx.y % gsub, b = blockIdx.z;
@@ -154,18 +163,16 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     split_range(a, split, t0, t1);
     const bool has_codes = t1 > t0;
 
-    const uint32_t lut_s = smem_u32(lut_p), vtab_s = smem_u32(vtab_p);
-
     // ---------------------------------------------------------------- prologue: V table + K LUT
     if (has_codes) {
         // The K gather table kT (64 KB, L2 resident) streams through the stage area in four 16 KB chunks (cp.async double
         // buffer); the V table (already in gather order) is copied straight to its place in the background.
-        const uint32_t stage0 = smem_u32(stage_p);
+        const uint32_t stage0 = smem_u32(stage_p), vtab_s = smem_u32(smem + kVtabOff);
         auto load_chunk = [&](int ch) {
             const char* src = reinterpret_cast<const char*>(prepared) + ch * 16384;
             const uint32_t dst = stage0 + (ch & 1) * 16384;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cp_async16(dst + (tid + i * kThreads) * 16, src + (tid + i * kThreads) * 16, 16);
+            for (int i = 0; i < 16384 / 16 / kThreads; ++i) cp_async16(dst + (tid + i * kThreads) * 16, src + (tid + i * kThreads) * 16, 16);
             cp_async_commit();
         };
         load_chunk(0);
@@ -222,8 +229,10 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     if (has_codes) {
         const int lq = lane & 15, hw = lane >> 4;
         const int rot = (lq + hw) & 15;
-        const uint32_t stage_s = smem_u32(stage_p) + warp * 2 * kStageBytes;
-        unsigned char* pbuf_w = pbuf_p + warp * kTile * 16;
+        unsigned char* ksp = stage_p + warp * kStageBytes;
+        unsigned char* vsp = ksp + kTile * kRowBytes;
+        unsigned char* pbuf_w = pbuf_p + warp * kTile * 8;
+        const uint32_t ks_s = smem_u32(ksp), vs_s = smem_u32(vsp);
         const uint8_t* kbase = a.k_codes + hb * a.k_head_stride;
         const uint8_t* vbase = a.v_codes + hb * a.v_head_stride;
 
@@ -251,31 +260,31 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         }
 
         const int n_tiles = (t1 - t0 + kTile - 1) / kTile;
-        auto issue = [&](int tile, int stg) {
-            // 32 tokens * 64 B for K and for V: 128 chunks of 16 B each -> 4 + 4 per lane
+        // one K buffer and one V buffer per warp; K(i+1) is requested right after QK(i), V(i+1) right after PV(i)
+        auto issue = [&](int tile, const uint8_t* gbase, uint32_t dst) {
             const int tok0 = t0 + tile * kTile;
-            const uint32_t dst = stage_s + stg * kStageBytes;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int chunk = lane + i * 32;            // 0..127
+                const int chunk = lane + i * 32;            // 0..127: 32 tokens * 4 chunks of 16 B
                 const int tok = tok0 + (chunk >> 2);
                 const int ok = (tile < n_tiles && tok < t1) ? 16 : 0;
-                const int64_t off = (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16;
-                cp_async16(dst + chunk * 16, kbase + off, ok);
-                cp_async16(dst + kTile * kRowBytes + chunk * 16, vbase + off, ok);
+                cp_async16(dst + chunk * 16, gbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
             }
             cp_async_commit();
         };
+        issue(warp, kbase, ks_s);
+        issue(warp, vbase, vs_s);
 
-        issue(warp, 0);
-        int stg = 0;
-        bool first = true;
-        for (int tile = warp; tile < n_tiles; tile += kWarps, stg ^= 1) {
-            issue(tile + kWarps, stg ^ 1);
-            cp_async_wait<1>();
+        __half2 acc[4][G];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[sl][g] = __float2half2_rn(0.f);
+        int since_flush = 0;
+
+        for (int tile = warp; tile < n_tiles; tile += kWarps) {
+            cp_async_wait<1>();          // pending [K(i), V(i)] -> K(i) landed
             __syncwarp();
-            const unsigned char* ksp = stage_p + (warp * 2 + stg) * kStageBytes;
-            const unsigned char* vsp = ksp + kTile * kRowBytes;
             const int tok = t0 + tile * kTile + lane;
             const bool valid = tok < t1;
 
@@ -283,91 +292,116 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
             float s[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) s[g] = 0.f;
+            uint32_t words[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) words[w] = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));   // word (w + rot) % 16 of my row
 #pragma unroll
             for (int w = 0; w < 16; ++w) {
-                // my token's code word number (w + rot) % 16
-                const uint32_t word = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));
 #pragma unroll
                 for (int bq = 0; bq < 4; ++bq) {
                     if constexpr (G == 4) {
-                        const uint32_t sel = (uint32_t)(4 + (bq & 1)) | ((uint32_t)bq << 4) | (6u << 8) | (6u << 12);
-                        const uint32_t ad = __byte_perm(word, koff[w], sel);          // (code << 8) | column offset
-                        const uint2 e = lds64(lut_p + (bq >> 1) * 65536, ad);
+                        constexpr uint32_t selc[4] = {0x6604u, 0x6615u, 0x6624u, 0x6635u};
+                        const uint32_t ad = __byte_perm(words[w], koff[w], selc[bq]);     // (code << 8) | column offset
+                        const uint2 e = (bq >> 1) ? gather64<kSmemBase + kLutOff + 65536>(ad) : gather64<kSmemBase + kLutOff>(ad);
                         fhadd2(s[0], s[1], e.x);
                         fhadd2(s[2], s[3], e.y);
                     } else {
                         // the two half-warps use different bytes in the same step so that all 32 lanes hit 32 banks
-                        const int bb_1 = (bq + 1) & 3;
-                        const uint32_t sel0 = (uint32_t)(4 + (bq & 1)) | ((uint32_t)bq << 4) | (6u << 8) | (6u << 12);
-                        const uint32_t sel1 = (uint32_t)(4 + (bb_1 & 1)) | ((uint32_t)bb_1 << 4) | (6u << 8) | (6u << 12);
-                        const uint32_t ad = __byte_perm(word, koff[w], hw ? sel1 : sel0);
-                        const uint32_t imm = (uint32_t)(((hw ? bb_1 : bq) >> 1) * 128);
-                        const uint32_t e = lds32(lut_p + imm, ad);
+                        constexpr uint32_t selc[4] = {0x6604u, 0x6615u, 0x6624u, 0x6635u};
+                        const int b1 = (bq + 1) & 3;
+                        const uint32_t ad = __byte_perm(words[w], koff[w], hw ? selc[b1] : selc[bq]) + (uint32_t)(((hw ? b1 : bq) >> 1) * 128);
+                        const uint32_t e = gather32<kSmemBase + kLutOff>(ad);
                         if constexpr (G == 2) fhadd2(s[0], s[1], e);
                         else s[0] += __uint_as_float(e);
                     }
                 }
             }
+            __syncwarp();                                   // every lane has read its K row
+            issue(tile + kWarps, kbase, ks_s);              // K(i+1) streams in during the PV phase
 #pragma unroll
             for (int g = 0; g < G; ++g) s[g] = valid ? s[g] * a.scale_log2 : -INFINITY;
 
             // ------------------------------------------------ online softmax (lazy max: rescale only when needed)
-            bool need = first;
+            bool need = false;
 #pragma unroll
             for (int g = 0; g < G; ++g) need = need || (s[g] > st.m[g] + kRescaleMargin);
             if (__any_sync(0xffffffffu, need)) {
+                // flush the packed-half PV accumulators first: they are relative to the old max
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float2 f = __half22float2(acc[sl][g]);
+                        st.o[sl][g][0] += f.x; st.o[sl][g][1] += f.y;
+                        acc[sl][g] = __float2half2_rn(0.f);
+                    }
+                since_flush = 0;
                 float nm[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) nm[g] = fmaxf(st.m[g], warp_max(s[g]));
-                state_rescale<G>(st, nm);
-                first = false;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (nm[g] > st.m[g]) {
+                        const float alpha = exp2_safe(st.m[g], nm[g]);
+                        st.l[g] *= alpha;
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl) { st.o[sl][g][0] *= alpha; st.o[sl][g][1] *= alpha; }
+                        st.m[g] = nm[g];
+                    }
+                }
             }
-            float p[G];
+            float p[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 p[g] = exp2_safe(s[g], st.m[g]);
                 st.l[g] += p[g];
             }
-            // p for the PV phase: half2(p_g, p_g), 16 bytes per token
-            {
-                uint4 pk = make_uint4(0, 0, 0, 0);
-                pk.x = as_u32(__float2half2_rn(p[0]));
-                if constexpr (G >= 2) pk.y = as_u32(__float2half2_rn(p[1]));
-                if constexpr (G == 4) { pk.z = as_u32(__float2half2_rn(p[2])); pk.w = as_u32(__float2half2_rn(p[3])); }
-                *reinterpret_cast<uint4*>(pbuf_w + lane * 16) = pk;
-            }
+            // p for the PV phase: 4 halves (8 bytes) per token
+            *reinterpret_cast<uint2*>(pbuf_w + lane * 8) = make_uint2(as_u32(__floats2half2_rn(p[0], p[1])), as_u32(__floats2half2_rn(p[2], p[3])));
+
+            cp_async_wait<1>();          // pending [V(i), K(i+1)] -> V(i) landed
             __syncwarp();
 
             // ------------------------------------------------ PV: half-warp per token, lane owns 4 sub-spaces
-            __half2 acc[4][G];
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl)
-#pragma unroll
-                for (int g = 0; g < G; ++g) acc[sl][g] = __float2half2_rn(0.f);
 #pragma unroll 4
             for (int jp = 0; jp < kTile / 2; ++jp) {
                 const int j = 2 * jp + hw;
                 const uint32_t word = lds32(vsp, j * kRowBytes + lq * 4);
-                const uint4 pk = lds128(pbuf_w, j * 16);
-                const uint32_t pr[4] = {pk.x, pk.y, pk.z, pk.w};
+                const uint2 pk = lds64(pbuf_w, j * 8);
+                const __half2 p01 = as_h2(pk.x), p23 = as_h2(pk.y);
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl) {
                     const uint32_t ad = __byte_perm(word, sl < 2 ? voff01 : voff23, vsel[sl]);
-                    const __half2 v = as_h2(lds32(vtab_p, ad));
-#pragma unroll
-                    for (int g = 0; g < G; ++g) acc[sl][g] = __hfma2(as_h2(pr[g]), v, acc[sl][g]);
+                    const __half2 v = as_h2(gather32<kSmemBase + kVtabOff>(ad));
+                    acc[sl][0] = __hfma2(__low2half2(p01), v, acc[sl][0]);
+                    if constexpr (G >= 2) acc[sl][1] = __hfma2(__high2half2(p01), v, acc[sl][1]);
+                    if constexpr (G == 4) {
+                        acc[sl][2] = __hfma2(__low2half2(p23), v, acc[sl][2]);
+                        acc[sl][3] = __hfma2(__high2half2(p23), v, acc[sl][3]);
+                    }
                 }
             }
+            __syncwarp();                                   // every lane is done with the V tile and the p slots
+            issue(tile + kWarps, vbase, vs_s);              // V(i+1) streams in during the next QK phase
+            if (++since_flush == 2) {                       // packed-half partial sums live for at most 2 tiles (32 terms)
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl)
+                for (int sl = 0; sl < 4; ++sl)
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float2 f = __half22float2(acc[sl][g]);
-                    st.o[sl][g][0] += f.x;
-                    st.o[sl][g][1] += f.y;
-                }
-            __syncwarp();
+                    for (int g = 0; g < G; ++g) {
+                        const float2 f = __half22float2(acc[sl][g]);
+                        st.o[sl][g][0] += f.x; st.o[sl][g][1] += f.y;
+                        acc[sl][g] = __float2half2_rn(0.f);
+                    }
+                since_flush = 0;
+            }
         }
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float2 f = __half22float2(acc[sl][g]);
+                st.o[sl][g][0] += f.x; st.o[sl][g][1] += f.y;
+            }
         cp_async_wait<0>();
     }
 
@@ -378,7 +412,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         const int lq = lane & 15, hw = lane >> 4;
 #pragma unroll
         for (int g = 0; g < G; ++g) st.l[g] = warp_sum(st.l[g]);
-        float o2[4][G][2];   // indexed by byte bb (sub-space 4*lq + bb) after the fold, valid in lanes hw = 0
+        float* wx = xch + warp * (G * 128 + 2 * G);
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl)
 #pragma unroll
@@ -386,29 +420,17 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     // partner (hw=1) slot (sl - 1) & 3 holds the same sub-space as my (hw=0) slot sl
-                    const float mine = st.o[sl][g][k];
                     const float theirs = __shfl_xor_sync(0xffffffffu, st.o[(sl + 3) & 3][g][k], 16);
-                    o2[sl][g][k] = mine + theirs;
+                    if (hw == 0) wx[g * 128 + 2 * (4 * lq + sl) + k] = st.o[sl][g][k] + theirs;
                 }
-        float* wx = xch + warp * (G * 128 + 2 * G);
-        if (hw == 0) {
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl)
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const int m = 4 * lq + sl;
-                    wx[g * 128 + 2 * m] = o2[sl][g][0];
-                    wx[g * 128 + 2 * m + 1] = o2[sl][g][1];
-                }
-        }
         if (lane == 0) {
 #pragma unroll
             for (int g = 0; g < G; ++g) { wx[G * 128 + g] = st.m[g]; wx[G * 128 + G + g] = st.l[g]; }
         }
     }
     __syncthreads();
-    {
-        // thread t -> dim t (128 threads = 128 dims), all G heads
+    if (tid < 128) {
+        // thread t -> dim t, all G heads
         for (int g = 0; g < G; ++g) {
             float mstar = -INFINITY;
 #pragma unroll
@@ -430,7 +452,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     // ---------------------------------------------------------------- fp16 window (exact attention), part index n_splits
     if (split == a.n_splits - 1) {
         __syncthreads();
-        float* S = xch;                 // G * 128 scores / probabilities (xch is free again)
+        float* S = xch;                 // G * 128 probabilities, then 2 * G * 128 partial outputs
         const int r = a.r;
         for (int i = tid; i < G * 128; i += kThreads)
             qs[i] = io<T>::to_f(reinterpret_cast<const T*>(a.q)[(int64_t)(b * a.nh + h0) * 128 + i]) * a.scale_log2;
@@ -440,12 +462,14 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         for (int g = 0; g < G; ++g) sc[g] = -INFINITY;
         if (tid < r) {
             const uint4* kr = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_res) + ((int64_t)hb * a.res_len + tid) * 128);
+            uint4 rowv[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) rowv[c] = __ldg(kr + c);
 #pragma unroll
             for (int g = 0; g < G; ++g) sc[g] = 0.f;
-#pragma unroll 4
+#pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const uint4 v = __ldg(kr + c);
-                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t wv[4] = {rowv[c].x, rowv[c].y, rowv[c].z, rowv[c].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 kf = io<T>::to_f2(wv[e]);
@@ -455,43 +479,54 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
                 }
             }
         }
-        __shared__ float red[33];
         float wm[G], wl[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             wm[g] = block_reduce<true>(sc[g], red);
             const float p = (tid < r) ? exp2_safe(sc[g], wm[g]) : 0.f;
             wl[g] = block_reduce<false>(p, red);
-            S[g * 128 + tid] = p;
+            if (tid < 128) S[g * 128 + tid] = p;
         }
         __syncthreads();
+        // PV: thread -> (dim = tid & 127, token parity = tid >> 7)
         float o[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) o[g] = 0.f;
-        const T* vr = reinterpret_cast<const T*>(a.v_res) + (int64_t)hb * a.res_len * 128 + tid;
-        for (int j = 0; j < r; ++j) {
+        const int dim = tid & 127, par = tid >> 7;
+        const T* vr = reinterpret_cast<const T*>(a.v_res) + (int64_t)hb * a.res_len * 128 + dim;
+#pragma unroll 8
+        for (int j = par; j < r; j += 2) {
             const float v = io<T>::to_f(vr[(int64_t)j * 128]);
 #pragma unroll
             for (int g = 0; g < G; ++g) o[g] = fmaf(S[g * 128 + j], v, o[g]);
         }
+        float* O2 = S + G * 128;
+        if (par == 1) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * n_parts + a.n_splits) * 130;
-            part[tid] = o[g];
-            if (tid == 0) { part[128] = wm[g]; part[129] = wl[g]; }
+            for (int g = 0; g < G; ++g) O2[g * 128 + dim] = o[g];
+        }
+        __syncthreads();
+        if (par == 0) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * n_parts + a.n_splits) * 130;
+                part[dim] = o[g] + O2[g * 128 + dim];
+                if (dim == 0) { part[128] = wm[g]; part[129] = wl[g]; }
+            }
         }
     }
 
     // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
-    if (last_cta_of_group(a.counters, hb, a.n_splits * gsub, &flag)) merge_group<T>(a, b, hk);
+    if (last_cta_of_group(a.counters, hb, a.n_splits * gsub, flag)) merge_group<T>(a, b, hk);
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
 template <typename T, int G>
 static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
-    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * 2 * kStageBytes + kWarps * kTile * 16;
-    static_assert(kWarps * 2 * kStageBytes >= (4 * 128 + kWarps * (4 * 128 + 8)) * sizeof(float), "stage area too small for the epilogue");
+    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + 256;
+    static_assert(kWarps * kStageBytes >= (4 * 128 + kWarps * (4 * 128 + 8)) * sizeof(float), "stage area too small for the epilogue");
+    static_assert(kWarps * kStageBytes >= 2 * 16384, "stage area too small for the LUT-build chunks");
     static bool configured = false;
     if (!configured) {
         MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
