@@ -22,10 +22,21 @@ struct AttnArgs {
     int64_t k_head_stride, v_head_stride, v_ld;
     int bs, nh, nh_k, d, M, C, nk, r, res_len;
     int v_layout, page_size, n_pages;
-    int n_splits;         // CTAs over the coded tokens; part index n_splits = the fp16 window
+    int n_splits;         // CTAs over the coded tokens
+    int n_parts;          // partial states per head: generic n_splits + 1 (window = extra part), fast n_splits
     int units_per_split;  // 16-token units per split
     float scale_log2;     // log2(e)/sqrt(d)
+    unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 8 globaltimer stamps per CTA
 };
+
+__device__ __forceinline__ void dbg_stamp(const AttnArgs& a, int slot) {
+    if (a.dbg_timing && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        a.dbg_timing[cta * 8 + slot] = t;
+    }
+}
 
 // tokens [begin, end) of split `s`
 __device__ __forceinline__ void split_range(const AttnArgs& a, int s, int& begin, int& end) {
@@ -43,47 +54,76 @@ __device__ __forceinline__ int v_code_at(const AttnArgs& a, int hb, int j, int m
     return a.v_codes[(page * a.M + m) * a.page_size + (j % a.page_size)];
 }
 
-// Merge the n_splits+1 partial states of every query head of group (b, hk) and write the result.
+// Merge the a.n_parts partial states of every query head of group (b, hk) and write the result.
 // Called by the last CTA of the group (after the ticket), all threads of the block participate.
 // Algebra of flash_decoding_reduce_kernel (Kernel.cuh:1249-1269) on un-normalised fp32 partials.
+// All heads are merged together in two rounds of independent loads (one for (m, l), one for o): a serial chain of L2
+// round trips per head and per part used to put 10 us on the tail of every batch-1 launch.
+// `scr` = shared scratch of kMergeScratch floats.
+constexpr int kMergeScratch = 3 * 2048 + 64;
 template <typename T>
-__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk) {
+__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, float* scr) {
     const int G = a.nh / a.nh_k;
-    const int n_parts = a.n_splits + 1;
+    const int n_parts = a.n_parts;
     const int stride = a.d + 2;
-    for (int g = 0; g < G; ++g) {
-        const int h = hk * G + g;
-        const float* base = a.parts + ((int64_t)(b * a.nh + h) * n_parts) * stride;
-        float mstar = -INFINITY;
-        for (int i = 0; i < n_parts; ++i) {
-            const float l = __ldcg(base + (int64_t)i * stride + a.d + 1);
-            const float m = __ldcg(base + (int64_t)i * stride + a.d);
-            if (l > 0.f) mstar = fmaxf(mstar, m);
+    float* mm = scr;               // [gc][n_parts] running max of each part
+    float* ll = scr + 2048;        // [gc][n_parts] denominators
+    float* ww = scr + 4096;        // [gc][n_parts] merge weights
+    float* hd = scr + 6144;        // [gc][2]: m*, den
+    int gc_max = 2048 / n_parts;
+    if (gc_max < 1) gc_max = 1;    // n_parts <= 1024 is enforced by the host
+    for (int g0 = 0; g0 < G; g0 += gc_max) {
+        const int gc = min(gc_max, G - g0);
+        const int h0 = hk * G + g0;
+        const float* base = a.parts + ((int64_t)(b * a.nh + h0) * n_parts) * stride;   // heads are contiguous
+        for (int idx = threadIdx.x; idx < gc * n_parts; idx += blockDim.x) {
+            mm[idx] = __ldcg(base + (int64_t)idx * stride + a.d);
+            ll[idx] = __ldcg(base + (int64_t)idx * stride + a.d + 1);
         }
-        float den = 0.f;
-        for (int i = 0; i < n_parts; ++i) {
-            const float l = __ldcg(base + (int64_t)i * stride + a.d + 1);
-            const float m = __ldcg(base + (int64_t)i * stride + a.d);
-            if (l > 0.f) den += l * exp2f(m - mstar);
-        }
-        for (int k = threadIdx.x; k < a.d; k += blockDim.x) {
-            float acc = 0.f;
+        __syncthreads();
+        if (threadIdx.x < gc) {
+            const int g = threadIdx.x;
+            float mstar = -INFINITY;
+            for (int i = 0; i < n_parts; ++i)
+                if (ll[g * n_parts + i] > 0.f) mstar = fmaxf(mstar, mm[g * n_parts + i]);
+            float den = 0.f;
             for (int i = 0; i < n_parts; ++i) {
-                const float l = __ldcg(base + (int64_t)i * stride + a.d + 1);
-                const float m = __ldcg(base + (int64_t)i * stride + a.d);
-                if (l > 0.f) acc += __ldcg(base + (int64_t)i * stride + k) * exp2f(m - mstar);
+                const float l = ll[g * n_parts + i];
+                const float w = (l > 0.f) ? exp2f(mm[g * n_parts + i] - mstar) : 0.f;
+                ww[g * n_parts + i] = w;
+                den += l * w;
             }
+            hd[2 * g] = mstar;
+            hd[2 * g + 1] = den;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < gc * a.d; idx += blockDim.x) {
+            const int g = idx / a.d, k = idx % a.d;
+            const float* src = base + (int64_t)g * n_parts * stride + k;
+            const float* w = ww + g * n_parts;
+            float acc = 0.f;
+            int i = 0;
+            for (; i + 8 <= n_parts; i += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(i + u) * stride);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = fmaf(v[u], w[i + u], acc);
+            }
+            for (; i < n_parts; ++i) acc = fmaf(__ldcg(src + (int64_t)i * stride), w[i], acc);
+            const int h = h0 + g;
             if (a.partial_out) {
                 a.partial_out[(int64_t)(b * a.nh + h) * stride + k] = acc;
+                if (k == 0) {
+                    a.partial_out[(int64_t)(b * a.nh + h) * stride + a.d] = hd[2 * g] * kLn2;   // natural-log units
+                    a.partial_out[(int64_t)(b * a.nh + h) * stride + a.d + 1] = hd[2 * g + 1];
+                }
             } else {
-                reinterpret_cast<T*>(a.out)[(int64_t)(b * a.nh + h) * a.d + k] =
-                    io<T>::from_f(den > 0.f ? acc / den : 0.f);
+                const float den = hd[2 * g + 1];
+                reinterpret_cast<T*>(a.out)[(int64_t)(b * a.nh + h) * a.d + k] = io<T>::from_f(den > 0.f ? acc / den : 0.f);
             }
         }
-        if (a.partial_out && threadIdx.x == 0) {
-            a.partial_out[(int64_t)(b * a.nh + h) * stride + a.d] = mstar * kLn2;  // natural-log units
-            a.partial_out[(int64_t)(b * a.nh + h) * stride + a.d + 1] = den;
-        }
+        __syncthreads();
     }
 }
 

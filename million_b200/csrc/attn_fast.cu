@@ -141,9 +141,8 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     unsigned char* pbuf_p = smem + kPbufOff;                             // kWarps * kTile * 8 bytes (4 halves per token)
     int* flag = reinterpret_cast<int*>(smem + kMiscOff);
     float* red = reinterpret_cast<float*>(smem + kMiscOff + 16);         // 33 floats
-    // after the main loop the stage buffers are dead: reuse them for the cross-warp merge and the window
-    float* qs = reinterpret_cast<float*>(stage_p);                       // 4 * 128 floats (window)
-    float* xch = qs + 4 * 128;                                           // kWarps * (G*128 + 2*G) floats
+    // after the main loop the stage buffers and p slots are dead: reuse them for the cross-warp combine and the merge
+    float* xch = reinterpret_cast<float*>(stage_p);                      // 2 * kWarps * G * 130 floats, then kMergeScratch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (smem_u32(smem) != kSmemBase) {
@@ -151,14 +150,13 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
             printf("million_b200: dynamic shared memory starts at 0x%x, expected 0x%x\n", smem_u32(smem), kSmemBase);
         __trap();
     }
+    dbg_stamp(a, 0);
     const int split = blockIdx.x;
     // blockIdx.y enumerates (kv head, 4-head sub-group) when the GQA group is larger than 4
     const int hk = blockIdx.y / gsub, sub = blockIdx.y % gsub, b = blockIdx.z;
     const int Gfull = a.nh / a.nh_k;
     const int h0 = hk * Gfull + sub * G;                                // first query head of this CTA
     const int hb = b * a.nh_k + hk;
-    const int n_parts = a.n_splits + 1;
-
     int t0, t1;
     split_range(a, split, t0, t1);
     const bool has_codes = t1 > t0;
@@ -221,6 +219,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         }
     }
     __syncthreads();
+    dbg_stamp(a, 1);
 
     // ---------------------------------------------------------------- main loop over this warp's tiles
     WarpState<G> st;
@@ -405,14 +404,53 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         cp_async_wait<0>();
     }
 
-    __syncthreads();   // every warp is done with its stage buffers (aliased below)
-    // ---------------------------------------------------------------- combine the warps of this CTA -> partial
-    // lane layout: slot sl of lane (hw, lq) holds sub-space 4*lq + ((sl + hw) & 3).  First fold hw=1 into hw=0.
+    // ---------------------------------------------------------------- my share of the fp16 window (exact attention)
+    // The r recent tokens are dealt out to the splits of the group (r/S tokens each, one token per warp at a time), so no
+    // CTA carries a long serial tail.  Lane owns dims 4*lane .. 4*lane+3.
+    float wm[G], wl[G], wo[G][4];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { wm[g] = -INFINITY; wl[g] = 0.f; wo[g][0] = wo[g][1] = wo[g][2] = wo[g][3] = 0.f; }
+    {
+        const int w0 = (int)((long long)a.r * split / a.n_splits), w1 = (int)((long long)a.r * (split + 1) / a.n_splits);
+        if (w0 + warp < w1) {
+            float qv[G][4];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint2 qr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.q) + (int64_t)(b * a.nh + h0 + g) * 128 + 4 * lane));
+                const float2 q01 = io<T>::to_f2(qr.x), q23 = io<T>::to_f2(qr.y);
+                qv[g][0] = q01.x * a.scale_log2; qv[g][1] = q01.y * a.scale_log2; qv[g][2] = q23.x * a.scale_log2; qv[g][3] = q23.y * a.scale_log2;
+            }
+            for (int t = w0 + warp; t < w1; t += kWarps) {
+                const int64_t row = ((int64_t)hb * a.res_len + t) * 128 + 4 * lane;
+                const uint2 kr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
+                const uint2 vr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
+                const float2 k01 = io<T>::to_f2(kr.x), k23 = io<T>::to_f2(kr.y);
+                const float2 v01 = io<T>::to_f2(vr.x), v23 = io<T>::to_f2(vr.y);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float sg = warp_sum(fmaf(qv[g][3], k23.y, fmaf(qv[g][2], k23.x, fmaf(qv[g][1], k01.y, qv[g][0] * k01.x))));
+                    const float nm = fmaxf(wm[g], sg);
+                    const float alpha = exp2_safe(wm[g], nm), pw = exp2f(sg - nm);
+                    wl[g] = wl[g] * alpha + pw;
+                    wo[g][0] = fmaf(pw, v01.x, wo[g][0] * alpha); wo[g][1] = fmaf(pw, v01.y, wo[g][1] * alpha);
+                    wo[g][2] = fmaf(pw, v23.x, wo[g][2] * alpha); wo[g][3] = fmaf(pw, v23.y, wo[g][3] * alpha);
+                    wm[g] = nm;
+                }
+            }
+        }
+    }
+
+    __syncthreads();   // every warp is done with its stage buffers and p slots (aliased below)
+    dbg_stamp(a, 2);
+    // ---------------------------------------------------------------- combine the warps of this CTA -> one partial state
+    // 2 * kWarps entries of [G*128 o | G m | G l]: entry w = coded tokens of warp w, entry kWarps + w = its window tokens.
+    // Coded layout: slot sl of lane (hw, lq) holds sub-space 4*lq + ((sl + hw) & 3); hw=1 is folded into hw=0 first.
+    constexpr int kEntry = (G * 130 + 3) & ~3;   // 16-byte aligned entries
     {
         const int lq = lane & 15, hw = lane >> 4;
 #pragma unroll
         for (int g = 0; g < G; ++g) st.l[g] = warp_sum(st.l[g]);
-        float* wx = xch + warp * (G * 128 + 2 * G);
+        float* wx = xch + warp * kEntry;
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl)
 #pragma unroll
@@ -423,101 +461,51 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
                     const float theirs = __shfl_xor_sync(0xffffffffu, st.o[(sl + 3) & 3][g][k], 16);
                     if (hw == 0) wx[g * 128 + 2 * (4 * lq + sl) + k] = st.o[sl][g][k] + theirs;
                 }
+        float* ww = xch + (kWarps + warp) * kEntry;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            *reinterpret_cast<float4*>(ww + g * 128 + 4 * lane) = make_float4(wo[g][0], wo[g][1], wo[g][2], wo[g][3]);
         if (lane == 0) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) { wx[G * 128 + g] = st.m[g]; wx[G * 128 + G + g] = st.l[g]; }
+            for (int g = 0; g < G; ++g) {
+                wx[G * 128 + g] = st.m[g]; wx[G * 128 + G + g] = st.l[g];
+                ww[G * 128 + g] = wm[g];   ww[G * 128 + G + g] = wl[g];
+            }
         }
     }
     __syncthreads();
-    if (tid < 128) {
-        // thread t -> dim t, all G heads
-        for (int g = 0; g < G; ++g) {
-            float mstar = -INFINITY;
+    {
+        // thread -> (dim = tid & 127, head half = tid >> 7)
+        constexpr int GH = G >= 2 ? G / 2 : 1;
+        const int dim = tid & 127, hsel = tid >> 7;
+        if (G >= 2 || hsel == 0) {
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) mstar = fmaxf(mstar, xch[w * (G * 128 + 2 * G) + G * 128 + g]);
-            float o = 0.f, l = 0.f;
+            for (int gi = 0; gi < GH; ++gi) {
+                const int g = (G >= 2 ? hsel * GH : 0) + gi;
+                float mstar = -INFINITY;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const float* wx = xch + w * (G * 128 + 2 * G);
-                const float sc = exp2_safe(wx[G * 128 + g], mstar);
-                o += wx[g * 128 + tid] * sc;
-                l += wx[G * 128 + G + g] * sc;
-            }
-            float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * n_parts + split) * 130;
-            part[tid] = o;
-            if (tid == 0) { part[128] = mstar; part[129] = l; }
-        }
-    }
-
-    // ---------------------------------------------------------------- fp16 window (exact attention), part index n_splits
-    if (split == a.n_splits - 1) {
-        __syncthreads();
-        float* S = xch;                 // G * 128 probabilities, then 2 * G * 128 partial outputs
-        const int r = a.r;
-        for (int i = tid; i < G * 128; i += kThreads)
-            qs[i] = io<T>::to_f(reinterpret_cast<const T*>(a.q)[(int64_t)(b * a.nh + h0) * 128 + i]) * a.scale_log2;
-        __syncthreads();
-        float sc[G];
+                for (int e = 0; e < 2 * kWarps; ++e) mstar = fmaxf(mstar, xch[e * kEntry + G * 128 + g]);
+                float o = 0.f, l = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) sc[g] = -INFINITY;
-        if (tid < r) {
-            const uint4* kr = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_res) + ((int64_t)hb * a.res_len + tid) * 128);
-            uint4 rowv[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) rowv[c] = __ldg(kr + c);
-#pragma unroll
-            for (int g = 0; g < G; ++g) sc[g] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const uint32_t wv[4] = {rowv[c].x, rowv[c].y, rowv[c].z, rowv[c].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 kf = io<T>::to_f2(wv[e]);
-#pragma unroll
-                    for (int g = 0; g < G; ++g)
-                        sc[g] = fmaf(kf.y, qs[g * 128 + c * 8 + e * 2 + 1], fmaf(kf.x, qs[g * 128 + c * 8 + e * 2], sc[g]));
+                for (int e = 0; e < 2 * kWarps; ++e) {
+                    const float* ex = xch + e * kEntry;
+                    const float sc = exp2_safe(ex[G * 128 + g], mstar);
+                    o = fmaf(ex[g * 128 + dim], sc, o);
+                    l = fmaf(ex[G * 128 + G + g], sc, l);
                 }
-            }
-        }
-        float wm[G], wl[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            wm[g] = block_reduce<true>(sc[g], red);
-            const float p = (tid < r) ? exp2_safe(sc[g], wm[g]) : 0.f;
-            wl[g] = block_reduce<false>(p, red);
-            if (tid < 128) S[g * 128 + tid] = p;
-        }
-        __syncthreads();
-        // PV: thread -> (dim = tid & 127, token parity = tid >> 7)
-        float o[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) o[g] = 0.f;
-        const int dim = tid & 127, par = tid >> 7;
-        const T* vr = reinterpret_cast<const T*>(a.v_res) + (int64_t)hb * a.res_len * 128 + dim;
-#pragma unroll 8
-        for (int j = par; j < r; j += 2) {
-            const float v = io<T>::to_f(vr[(int64_t)j * 128]);
-#pragma unroll
-            for (int g = 0; g < G; ++g) o[g] = fmaf(S[g * 128 + j], v, o[g]);
-        }
-        float* O2 = S + G * 128;
-        if (par == 1) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) O2[g * 128 + dim] = o[g];
-        }
-        __syncthreads();
-        if (par == 0) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * n_parts + a.n_splits) * 130;
-                part[dim] = o[g] + O2[g * 128 + dim];
-                if (dim == 0) { part[128] = wm[g]; part[129] = wl[g]; }
+                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * a.n_parts + split) * 130;
+                part[dim] = o;
+                if (dim == 0) { part[128] = mstar; part[129] = l; }
             }
         }
     }
-
+    dbg_stamp(a, 3);
+    dbg_stamp(a, 4);
     // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
-    if (last_cta_of_group(a.counters, hb, a.n_splits * gsub, flag)) merge_group<T>(a, b, hk);
+    const bool last = last_cta_of_group(a.counters, hb, a.n_splits * gsub, flag);
+    dbg_stamp(a, 5);
+    if (last) merge_group<T>(a, b, hk, xch);
+    dbg_stamp(a, 6);
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
@@ -525,8 +513,9 @@ template <typename T, int G>
 static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
     const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + 256;
-    static_assert(kWarps * kStageBytes >= (4 * 128 + kWarps * (4 * 128 + 8)) * sizeof(float), "stage area too small for the epilogue");
+    static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= 2 * kWarps * 4 * 130 * sizeof(float), "stage + p area too small for the combine");
     static_assert(kWarps * kStageBytes >= 2 * 16384, "stage area too small for the LUT-build chunks");
+    static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static bool configured = false;
     if (!configured) {
         MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -538,7 +527,9 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
     return MILLION_OK;
 }
 
-int launch_attn_fast(const AttnArgs& a, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only) {
+int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only) {
+    AttnArgs a = a_in;
+    a.n_parts = a.n_splits;   // the window is dealt out to the splits, no extra part
     const int Gfull = a.nh / a.nh_k;
     if (a.d != 128 || a.M != 64 || a.C != 256) MILLION_UNSUPPORTED("fast decode attention needs d=128, M=64, C=256");
     if (!(Gfull == 1 || Gfull == 2 || Gfull % 4 == 0)) MILLION_UNSUPPORTED("fast decode attention needs nh/nh_k in {1,2,4k}");

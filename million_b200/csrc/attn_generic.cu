@@ -15,12 +15,13 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
     float* lut = reinterpret_cast<float*>(smem_raw);  // M*C (coded splits) or d (window: q)
     __shared__ float P[128];
     __shared__ float red[33];
+    __shared__ float mscr[kMergeScratch];
     __shared__ int flag;
 
     const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x;
     const int G = a.nh / a.nh_k, dm = a.d / a.M, hb = b * a.nh_k + hk;
-    const int n_parts = a.n_splits + 1;
+    const int n_parts = a.n_parts;
     const bool window = (split == a.n_splits);
     const T* kcent = reinterpret_cast<const T*>(a.k_cent);
     const T* vcent = reinterpret_cast<const T*>(a.v_cent);
@@ -99,10 +100,12 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
             if (tid + u * 128 < a.d) part[tid + u * 128] = acc[u];
         if (tid == 0) { part[a.d] = run_m; part[a.d + 1] = run_l; }
     }
-    if (last_cta_of_group(a.counters, hb, n_parts, &flag)) merge_group<T>(a, b, hk);
+    if (last_cta_of_group(a.counters, hb, n_parts, &flag)) merge_group<T>(a, b, hk, mscr);
 }
 
-int launch_attn_generic(const AttnArgs& a, int io_dtype, cudaStream_t stream) {
+int launch_attn_generic(const AttnArgs& a_in, int io_dtype, cudaStream_t stream) {
+    AttnArgs a = a_in;
+    a.n_parts = a.n_splits + 1;
     if (a.d > 256) MILLION_UNSUPPORTED("generic decode attention supports d <= 256 (got %d)", a.d);
     const size_t smem = sizeof(float) * (size_t)max(a.M * a.C, a.d);
     dim3 grid(a.n_splits + 1, a.nh_k, a.bs), block(128);

@@ -45,6 +45,7 @@ int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float* cent, 
                     int64_t cts, int64_t cms, int64_t t0, const int64_t* page_ids, int64_t pihs, int page_size, int n_heads,
                     int n_tokens, int d, int M, int C, int impl, cudaStream_t stream);
 
+static unsigned long long* g_dbg_timing = nullptr;
 static inline int elem_bytes(int dtype) { return dtype == MILLION_F32 ? 4 : 2; }
 
 }  // namespace million
@@ -115,16 +116,28 @@ int million_pq_codebook_prepare(const void* k_cent, const void* v_cent, int dtyp
     return launch_codebook_prepare(k_cent, v_cent, dtype, prepared, (cudaStream_t)stream);
 }
 
+// Cost of the fp16 window and of the per-CTA prologue (LUT build) in units of 16 coded tokens (measured on B200)
+static const int kWindowUnits = 0, kPrologueUnits = 44;   // ~4.5 us of per-CTA prologue + epilogue at ~0.1 us per unit
+
 int million_pq_decode_attn_default_splits(int bs, int nh_k, int nk) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int groups = bs * nh_k > 0 ? bs * nh_k : 1;
-    // one CTA per SM: fill the machine once, never fewer than 128 coded tokens per split
-    int s = sms / groups;
-    if (s < 1) s = 1;
-    const int max_by_len = (nk + 127) / 128;
-    if (s > max_by_len) s = max_by_len;
-    if (s < 1) s = 1;
-    return s;
+    const int units = (nk + 15) / 16 + kWindowUnits;
+    // One CTA per SM at a time.  Pick the split count S that minimises waves(S) * (units/S + prologue): more, smaller
+    // splits fill partial waves better (64 groups: S=2 uses 128 of 148 SMs, S=9 fills 3.9 of 4 waves) but pay the LUT
+    // build once per CTA.  Never fewer than 128 coded tokens per split.
+    int max_s = (nk + 127) / 128;
+    if (max_s < 1) max_s = 1;
+    if (max_s > 64) max_s = 64;
+    int best_s = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= max_s; ++s) {
+        const int ctas = groups * s;
+        const int waves = (ctas + sms - 1) / sms;
+        const double cost = (double)waves * ((double)((units + s - 1) / s) + kPrologueUnits);
+        if (cost < best_cost * 0.995) { best_cost = cost; best_s = s; }
+    }
+    return best_s;
 }
 
 int64_t million_pq_decode_attn_workspace_bytes(int bs, int nh, int nh_k, int d, int max_splits) {
@@ -172,7 +185,9 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     const int units = (p->nk + 15) / 16;
     a.units_per_split = (units + S - 1) / S;
     if (a.units_per_split < 1) a.units_per_split = 1;
+    MILLION_REQUIRE(S + 1 <= 1024, "attn: at most 1023 splits");
     a.scale_log2 = kLog2e / sqrtf((float)p->d);
+    a.dbg_timing = g_dbg_timing;
 
     cudaStream_t st = (cudaStream_t)stream;
     if (p->impl == MILLION_IMPL_GENERIC) return launch_attn_generic(a, p->io_dtype, st);
@@ -181,6 +196,9 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
         return launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, false);
     return launch_attn_generic(a, p->io_dtype, st);
 }
+
+/* debug hook (not part of the public header): per-CTA phase time stamps of the decode-attention kernels */
+void million_debug_set_timing_buffer(void* buf) { g_dbg_timing = reinterpret_cast<unsigned long long*>(buf); }
 
 int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, million_stream_t stream) {
     MILLION_REQUIRE(parts && out && n_parts > 0 && n_rows >= 0 && d > 0, "lse_merge: bad arguments");
