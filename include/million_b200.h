@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MILLION_ABI_VERSION 2
+#define MILLION_ABI_VERSION 3
 
 typedef void* million_stream_t; /* cudaStream_t */
 
@@ -84,8 +84,16 @@ int million_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *             row-major cache (bs,nh_k,cap,M): token_stride=M, m_stride=1; transposed (bs,nh_k,M,cap):
  *             token_stride=1, m_stride=cap.  code_bytes = 1 (C<=256) or 2 (C<=65536, nbits2dtype).
  */
+/* Optional operand tiles for the tensor-core (tcgen05) encoder: the codebook as [-2c | |c|^2 split] rows in the
+ * input format, per-sub-space max |c|^2, and a representability check (synchronous, one-time per codebook and input
+ * dtype).  Returns MILLION_ERR_UNSUPPORTED when the shape is not covered (needs C=256, d/M in {2,4}, M % 16 == 0,
+ * fp16/bf16 input) or the centroids are not exactly representable in the input format; callers then pass NULL and
+ * the exact CUDA-core encoder runs. */
+int64_t million_pq_encoder_prepared_bytes(int d, int M, int C);
+int million_pq_encoder_prepare(const float* cent, int x_dtype, int d, int M, int C, void* prepared, million_stream_t stream);
+
 int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride,
-                      const float* cent,
+                      const float* cent, const void* prepared_encoder /* may be NULL */,
                       void* codes, int code_bytes,
                       int64_t codes_head_stride, int64_t codes_token_stride, int64_t codes_m_stride,
                       int64_t t0,
@@ -96,7 +104,7 @@ int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride,
  * token (t0+t) of head `head` goes to pool[page_ids[head*page_ids_head_stride + (t0+t)/page_size], m, (t0+t)%page_size].
  * Format: dynamic_paged_pq_utils.py:46-48, 768-811. */
 int million_pq_encode_paged(const void* x, int x_dtype, int64_t x_head_stride,
-                            const float* cent,
+                            const float* cent, const void* prepared_encoder /* may be NULL */,
                             uint8_t* page_pool, const int64_t* page_ids, int64_t page_ids_head_stride,
                             int page_size, int64_t t0,
                             int n_heads, int n_tokens, int d, int M, int C,

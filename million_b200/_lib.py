@@ -13,7 +13,7 @@ MILLION_OK, MILLION_ERR_INVALID, MILLION_ERR_UNSUPPORTED, MILLION_ERR_CUDA = 0, 
 V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_FAST = 0, 1, 2
 ATTN_PARTIAL_ONLY = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
 
@@ -44,9 +44,11 @@ SIGNATURES = {
     "million_abi_version": (ctypes.c_int, []),
     "million_last_error": (ctypes.c_char_p, []),
     "million_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
-    "million_pq_encode": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int, c_i64, c_i64, c_i64, c_i64,
+    "million_pq_encoder_prepared_bytes": (c_i64, [ctypes.c_int] * 3),
+    "million_pq_encoder_prepare": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "million_pq_encode": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, ctypes.c_int, c_i64, c_i64, c_i64, c_i64,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
-    "million_pq_encode_paged": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_i64,
+    "million_pq_encode_paged": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_i64,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "million_pq_decode": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, ctypes.c_int, c_i64,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "attn_common.cuh"
+#include "codec.cuh"
 
 namespace million {
 
@@ -32,7 +33,6 @@ int sm_count() {
     return cached[dev];
 }
 
-struct CodeDst;
 int launch_attn_generic(const AttnArgs& a, int io_dtype, cudaStream_t stream);
 int launch_attn_fast(const AttnArgs& a, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only);
 int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, void* out, cudaStream_t stream);
@@ -41,9 +41,23 @@ int launch_reconstruct(const void* codes, int code_bytes, int64_t chs, int64_t c
                        int dtype, int64_t ohs, int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream);
 int launch_rows_copy2(void* k_dst, void* v_dst, int64_t dst_hs_b, int64_t dst_off_b, const void* k_src, const void* v_src,
                       int64_t src_hs_b, int64_t src_off_b, int n_heads, int64_t bytes_per_head, cudaStream_t stream);
-int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float* cent, void* codes, int code_bytes, int64_t chs,
-                    int64_t cts, int64_t cms, int64_t t0, const int64_t* page_ids, int64_t pihs, int page_size, int n_heads,
-                    int n_tokens, int d, int M, int C, int impl, cudaStream_t stream);
+int64_t encode_tc_prepared_bytes(int d, int M, int C);
+int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C, void* out, cudaStream_t stream);
+int launch_encode_tc(const void* x, int x_dtype, int64_t xhs, const float* cent, const void* prepared, const CodeDst& dst,
+                     int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream, bool probe_only);
+
+static int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float* cent, const void* prepared, void* codes, int code_bytes,
+                           int64_t chs, int64_t cts, int64_t cms, int64_t t0, const int64_t* page_ids, int64_t pihs, int page_size,
+                           int n_heads, int n_tokens, int d, int M, int C, int impl, cudaStream_t stream) {
+    CodeDst dst{codes, code_bytes, chs, cts, cms, t0, page_ids, pihs, page_size, M};
+    if (impl == MILLION_IMPL_GENERIC) return launch_encode_generic(x, x_dtype, xhs, cent, dst, n_heads, n_tokens, d, M, C, stream);
+    if (impl == MILLION_IMPL_FAST) return launch_encode_tc(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, false);
+    // AUTO: the tensor-core encoder pays off from a few hundred vectors on
+    if ((int64_t)n_heads * n_tokens >= 256 &&
+        launch_encode_tc(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, true) == MILLION_OK)
+        return launch_encode_tc(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, false);
+    return launch_encode_generic(x, x_dtype, xhs, cent, dst, n_heads, n_tokens, d, M, C, stream);
+}
 
 static unsigned long long* g_dbg_timing = nullptr;
 static inline int elem_bytes(int dtype) { return dtype == MILLION_F32 ? 4 : 2; }
@@ -68,7 +82,14 @@ int million_device_info(int* sms, int* major, int* minor) {
     return MILLION_OK;
 }
 
-int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, void* codes, int code_bytes,
+int64_t million_pq_encoder_prepared_bytes(int d, int M, int C) { return encode_tc_prepared_bytes(d, M, C); }
+
+int million_pq_encoder_prepare(const float* cent, int x_dtype, int d, int M, int C, void* prepared, million_stream_t stream) {
+    MILLION_REQUIRE(cent && prepared, "encoder_prepare: null pointer");
+    return launch_encode_tc_prepare(cent, x_dtype, d, M, C, prepared, (cudaStream_t)stream);
+}
+
+int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, const void* prepared, void* codes, int code_bytes,
                       int64_t codes_head_stride, int64_t codes_token_stride, int64_t codes_m_stride, int64_t t0,
                       int n_heads, int n_tokens, int d, int M, int C, int impl, million_stream_t stream) {
     MILLION_REQUIRE(n_heads >= 0 && n_tokens >= 0, "encode: negative sizes");
@@ -77,11 +98,11 @@ int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride, const f
     MILLION_REQUIRE(M > 0 && d > 0 && d % M == 0 && C > 1, "encode: need d %% M == 0 and C > 1 (d=%d M=%d C=%d)", d, M, C);
     MILLION_REQUIRE(code_bytes == 1 || code_bytes == 2, "encode: code_bytes must be 1 or 2");
     MILLION_REQUIRE(C <= (code_bytes == 1 ? 256 : 65536), "encode: C=%d does not fit %d-byte codes", C, code_bytes);
-    return encode_dispatch(x, x_dtype, x_head_stride, cent, codes, code_bytes, codes_head_stride, codes_token_stride,
+    return encode_dispatch(x, x_dtype, x_head_stride, cent, prepared, codes, code_bytes, codes_head_stride, codes_token_stride,
                            codes_m_stride, t0, nullptr, 0, 0, n_heads, n_tokens, d, M, C, impl, (cudaStream_t)stream);
 }
 
-int million_pq_encode_paged(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, uint8_t* page_pool,
+int million_pq_encode_paged(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, const void* prepared, uint8_t* page_pool,
                             const int64_t* page_ids, int64_t page_ids_head_stride, int page_size, int64_t t0, int n_heads,
                             int n_tokens, int d, int M, int C, int impl, million_stream_t stream) {
     MILLION_REQUIRE(n_heads >= 0 && n_tokens >= 0, "encode_paged: negative sizes");
@@ -89,7 +110,7 @@ int million_pq_encode_paged(const void* x, int x_dtype, int64_t x_head_stride, c
     MILLION_REQUIRE(x && cent && page_pool && page_ids, "encode_paged: null pointer");
     MILLION_REQUIRE(M > 0 && d > 0 && d % M == 0 && C > 1 && C <= 256, "encode_paged: bad d/M/C (%d/%d/%d)", d, M, C);
     MILLION_REQUIRE(page_size > 0, "encode_paged: page_size must be positive");
-    return encode_dispatch(x, x_dtype, x_head_stride, cent, page_pool, 1, 0, 0, 0, t0, page_ids, page_ids_head_stride,
+    return encode_dispatch(x, x_dtype, x_head_stride, cent, prepared, page_pool, 1, 0, 0, 0, t0, page_ids, page_ids_head_stride,
                            page_size, n_heads, n_tokens, d, M, C, impl, (cudaStream_t)stream);
 }
 

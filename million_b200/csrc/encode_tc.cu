@@ -1,0 +1,443 @@
+// encode_tc.cu — PQ encoder whose distance contraction runs on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Replaces sa_encode_4d_keops (scripts/utils/pq_utils.py:451-499): code[t, m] = argmin_c sum_k (x[t,m,k] - C[m,c,k])^2.
+//
+// For one sub-space m the 128 x 256 distance tile of a 128-token block is ONE tcgen05.mma (M=128, N=256, K=16):
+//     A[t]  = [ x_0 .. x_{dm-1},  1,     1,      1,     0 .. ]   (16 bytes per token, written by CUDA cores)
+//     B[c]  = [ -2c_0 .. -2c_{dm-1}, n_hi, n_mid, n_lo, 0 .. ]   (16 bytes per centroid, resident in shared memory)
+//     D[t][c] = |c|^2 - 2 x.c   (fp32 in TMEM; |c|^2 split into three terms of the input format)
+// The second K chunk (k = 8..15) of both operands is a shared block of zeros reached through the descriptor's
+// leading-dimension offset, so an operand row really is 16 bytes.  D lives in TMEM (2 x 256 columns, double buffered:
+// the MMA of item i+1 runs while the CUDA cores reduce item i).
+//
+// The epilogue reads D with tcgen05.ld and does NOT trust it for the final answer: |c|^2 - 2x.c cancels badly when x
+// is close to c, and the reference's arithmetic is the direct (x-c)^2 in fp32.  D is used as a FILTER: every centroid
+// within eps = 2^-17 (|x|^2 + max|c|^2) of the row minimum is a candidate (min via FMNMX3, candidate bits via
+// FADD + funnel shift); one candidate -> that is the code; several (about 1e-4 of the cases) or none -> the exact fp32
+// formula of the oracle is evaluated over the candidates, first minimum wins.  Codes are therefore bit-identical to
+// the generic encoder and the oracle, ties included.
+//
+// Shapes: C = 256, d/M in {2, 4}, x in fp16/bf16, centroids representable in x's format (checked by the prepare step).
+#include <type_traits>
+
+#include "codec.cuh"
+
+namespace million {
+namespace tc {
+
+constexpr int kThreads = 256;
+constexpr int kTokTile = 128;
+constexpr int kMG = 16;                    // sub-spaces per CTA: 16 B tiles of 4 KB stay resident
+constexpr int kBTileBytes = 256 * 16;      // 4 KB per sub-space
+constexpr int kATileBytes = kTokTile * 16; // 2 KB per item
+constexpr int kZeroBytes = 4096;
+constexpr float kEpsScale = 7.62939453125e-06f;   // 2^-17
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier / tcgen05 wrappers (PTX ISA 8.6+, sm_100a)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] = A[smem] * B[smem]^T, one K=16 step, no accumulation
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; SBO = bytes between row blocks, LBO = bytes between K chunks
+__device__ __forceinline__ uint64_t make_desc(uint32_t start, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((start >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+    return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// 64 consecutive fp32 columns of my TMEM lane
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
+          "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
+          "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// row minimum of 64 values and, relative to thr = min(best_so_far, that minimum) + eps, the candidate bits
+// (bit 31 of word 0 = first column).  Returns the chunk minimum.
+__device__ __forceinline__ float reduce_chunk(const float (&v)[64], float best_so_far, float eps, uint32_t& w0, uint32_t& w1) {
+    float m = v[0];
+#pragma unroll
+    for (int i = 1; i + 1 < 64; i += 2) m = min3(m, v[i], v[i + 1]);
+    m = fminf(m, v[63]);
+    const float thr = fminf(best_so_far, m) + eps;
+    w0 = 0; w1 = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w0 = __funnelshift_l(__float_as_uint(v[i] - thr), w0, 1);        // sign(v - thr) = 1 <=> v < thr
+#pragma unroll
+    for (int i = 32; i < 64; ++i) w1 = __funnelshift_l(__float_as_uint(v[i] - thr), w1, 1);
+    return m;
+}
+
+struct EncArgs {
+    const void* x;
+    int64_t x_head_stride;
+    const unsigned char* prep;   // B tiles (M * 4 KB) | cmax2 (M floats) | flag
+    const float* cent;           // (M, 256, DM) fp32 — exact re-check
+    CodeDst dst;
+    int n_heads, n_tokens, d, M, tiles_per_head, total_tiles;
+};
+
+// exact oracle arithmetic for one centroid
+template <int DM>
+__device__ __forceinline__ float exact_dist(const float (&xv)[DM], const float* c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < DM; ++k) {
+        const float diff = __fsub_rn(xv[k], c[k]);
+        const float sq = __fmul_rn(diff, diff);
+        acc = (k == 0) ? sq : __fadd_rn(acc, sq);
+    }
+    return acc;
+}
+
+template <typename T, int DM>
+__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* Bs = smem;                                   // kMG * 4 KB
+    unsigned char* As = Bs + kMG * kBTileBytes;                 // 2 slots * 2 KB
+    unsigned char* Zs = As + 2 * kATileBytes;                   // 4 KB of zeros (second K chunk of both operands)
+    float* xch = reinterpret_cast<float*>(Zs + kZeroBytes);     // 256 threads * 5 words
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kThreads * 5);   // 2 mbarriers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    float* cmax_s = reinterpret_cast<float*>(tmem_slot + 2);    // kMG floats
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * kMG;
+    constexpr uint32_t kOne = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
+    constexpr uint32_t kFmt = std::is_same<T, __half>::value ? 0u : 1u;
+    // instruction descriptor: D fp32, A/B format, both K-major, N = 256, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+    // ---- one-time setup
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (tid == 32) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.prep + (int64_t)m0 * kBTileBytes);
+        uint4* dstB = reinterpret_cast<uint4*>(Bs);
+        for (int i = tid; i < kMG * kBTileBytes / 16; i += kThreads) dstB[i] = __ldg(src + i);
+        uint4* z = reinterpret_cast<uint4*>(Zs);
+        for (int i = tid; i < kZeroBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        if (tid < kMG) cmax_s[tid] = reinterpret_cast<const float*>(a.prep + (int64_t)a.M * kBTileBytes)[m0 + tid];
+    }
+    fence_async_proxy();        // generic-proxy writes (B, zeros) -> visible to the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t zs = smem_u32(Zs);
+
+    // my TMEM view: lanes 32*(warp%4) .., columns 128*(warp/4) .. of the active buffer
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;              // token row inside the tile handled by this thread (both halves)
+
+    auto issue_mma = [&](int slot, int j) {
+        const uint32_t as = smem_u32(As + slot * kATileBytes), bs = smem_u32(Bs + j * kBTileBytes);
+        umma_f16(tmem_base + slot * 256, make_desc(as, zs - as, 128), make_desc(bs, zs - bs, 128), idesc);
+        umma_commit(smem_u32(&bars[slot]));
+    };
+
+    uint32_t it = 0;                            // running item counter of this CTA (slot = it & 1, parity = (it >> 1) & 1)
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int head = tile / a.tiles_per_head;
+        const int tok = (tile % a.tiles_per_head) * kTokTile + row;
+        const bool live = tok < a.n_tokens;
+        // my token's values for the kMG sub-spaces of this CTA: kMG * DM halves
+        uint32_t xr[kMG * DM / 2];
+        {
+            const T* xp = reinterpret_cast<const T*>(a.x) + head * a.x_head_stride + (int64_t)(live ? tok : 0) * a.d + m0 * DM;
+            const uint4* xp4 = reinterpret_cast<const uint4*>(xp);
+#pragma unroll
+            for (int i = 0; i < kMG * DM / 8; ++i) {
+                uint4 v = live ? __ldg(xp4 + i) : make_uint4(0, 0, 0, 0);
+                xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+            }
+        }
+        auto build_A = [&](int slot, int j) {
+            if (half == 0) {   // one writer per token row
+                uint4 rowv;
+                if constexpr (DM == 2) rowv = make_uint4(xr[j], kOne | (kOne << 16), kOne, 0u);
+                else rowv = make_uint4(xr[2 * j], xr[2 * j + 1], kOne | (kOne << 16), kOne);
+                *reinterpret_cast<uint4*>(As + slot * kATileBytes + row * 16) = rowv;
+            }
+        };
+        uint32_t codes[kMG / 4] = {0, 0, 0, 0};
+
+        // ---- software pipeline over the kMG items of this tile (the pipeline drains at the end of every tile)
+        build_A(it & 1, 0);
+        fence_async_proxy();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) issue_mma(it & 1, 0);
+
+#pragma unroll
+        for (int j = 0; j < kMG; ++j, ++it) {
+            const int slot = it & 1;
+            if (j + 1 < kMG) {
+                // the other slot/buffer is free: MMA(it-1) was waited for and its D was read before the last barrier
+                build_A(slot ^ 1, j + 1);
+                fence_async_proxy();
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
+                if (tid == 0) issue_mma(slot ^ 1, j + 1);
+            }
+            mbar_wait(smem_u32(&bars[slot]), (it >> 1) & 1);
+            tc_fence_after();
+
+            // |x_m|^2 and the filter width
+            float xv[DM];
+            if constexpr (DM == 2) {
+                const float2 f = io<T>::to_f2(xr[j]);
+                xv[0] = f.x; xv[1] = f.y;
+            } else {
+                const float2 f0 = io<T>::to_f2(xr[2 * j]), f1 = io<T>::to_f2(xr[2 * j + 1]);
+                xv[0] = f0.x; xv[1] = f0.y; xv[2] = f1.x; xv[3] = f1.y;
+            }
+            float x2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < DM; ++k) x2 = fmaf(xv[k], xv[k], x2);
+            const float eps = (x2 + cmax_s[j]) * kEpsScale;
+
+            // ---- epilogue: 128 columns of my row, two chunks of 64
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + half * 128;
+            float v[64];
+            uint32_t w[4];
+            tmem_ld64(taddr, v);
+            const float mn0 = reduce_chunk(v, INFINITY, eps, w[0], w[1]);
+            tmem_ld64(taddr + 64, v);
+            const float mn1 = reduce_chunk(v, mn0, eps, w[2], w[3]);
+            tc_fence_before();
+            const float mh = fminf(mn0, mn1);
+            if (mn0 > mh + eps) { w[0] = 0; w[1] = 0; }     // chunk 0 was filtered against a looser threshold
+            float* me = xch + tid * 5;
+            me[0] = mh;
+            me[1] = __uint_as_float(w[0]); me[2] = __uint_as_float(w[1]); me[3] = __uint_as_float(w[2]); me[4] = __uint_as_float(w[3]);
+            __syncthreads();
+            if (half == 0) {
+                const float* other = xch + (tid + 128) * 5;
+                const float mo = other[0];
+                const float mstar = fminf(mh, mo);
+                uint32_t cw[8];
+                const bool keep0 = !(mh > mstar + eps), keep1 = !(mo > mstar + eps);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cw[i] = keep0 ? w[i] : 0u;
+                    cw[4 + i] = keep1 ? __float_as_uint(other[1 + i]) : 0u;
+                }
+                int cnt = 0, code = 0;
+#pragma unroll
+                for (int i = 7; i >= 0; --i) {
+                    cnt += __popc(cw[i]);
+                    if (cw[i]) code = 32 * i + __clz(cw[i]);      // lowest candidate column
+                }
+                if (cnt != 1 && live) {
+                    // rare: several centroids inside the filter width (or a degenerate all-zero row): exact fp32 arg-min
+                    const float* cm = a.cent + (int64_t)(m0 + j) * 256 * DM;
+                    float best = INFINITY;
+                    int bi = 0;
+                    if (cnt == 0) {
+                        for (int c = 0; c < 256; ++c) {
+                            float cv[DM];
+#pragma unroll
+                            for (int k = 0; k < DM; ++k) cv[k] = __ldg(cm + c * DM + k);
+                            const float dd = exact_dist<DM>(xv, cv);
+                            if (dd < best) { best = dd; bi = c; }
+                        }
+                    } else {
+                        for (int i = 0; i < 8; ++i) {
+                            uint32_t bits = cw[i];
+                            while (bits) {
+                                const int lz = __clz(bits);
+                                bits &= ~(0x80000000u >> lz);
+                                const int c = 32 * i + lz;
+                                float cv[DM];
+#pragma unroll
+                                for (int k = 0; k < DM; ++k) cv[k] = __ldg(cm + c * DM + k);
+                                const float dd = exact_dist<DM>(xv, cv);
+                                if (dd < best) { best = dd; bi = c; }
+                            }
+                        }
+                    }
+                    code = bi;
+                }
+                codes[j >> 2] |= (uint32_t)code << (8 * (j & 3));
+            }
+        }
+        // ---- store the kMG codes of my token
+        if (half == 0 && live) {
+#pragma unroll
+            for (int j = 0; j < kMG; ++j) a.dst.put(head, tok, m0 + j, (codes[j >> 2] >> (8 * (j & 3))) & 0xff);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ prepare
+// B tiles: row c of sub-space m = [-2c_0 .. -2c_{dm-1}, n_hi, n_mid, n_lo, 0 ..] in T; cmax2[m] = max_c |c|^2; flag = 0 when a
+// centroid component (or its double) is not representable in T.
+template <typename T, int DM>
+__global__ void encode_prepare_kernel(const float* __restrict__ cent, unsigned char* __restrict__ out, int M) {
+    const int m = blockIdx.x, c = threadIdx.x;   // 256 threads
+    __shared__ float red[256];
+    const float* cv = cent + ((int64_t)m * 256 + c) * DM;
+    T row[8];
+    double n2 = 0.0;
+    bool exact = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) row[k] = io<T>::from_f(0.f);
+#pragma unroll
+    for (int k = 0; k < DM; ++k) {
+        const float v = cv[k];
+        row[k] = io<T>::from_f(-2.f * v);
+        exact = exact && (io<T>::to_f(row[k]) == -2.f * v) && (io<T>::to_f(io<T>::from_f(v)) == v);
+        n2 += (double)v * (double)v;
+    }
+    const T hi = io<T>::from_f((float)n2);
+    const double r1 = n2 - (double)io<T>::to_f(hi);
+    const T mid = io<T>::from_f((float)r1);
+    const double r2 = r1 - (double)io<T>::to_f(mid);
+    const T lo = io<T>::from_f((float)r2);
+    row[DM] = hi; row[DM + 1] = mid; row[DM + 2] = lo;
+    *reinterpret_cast<uint4*>(out + ((int64_t)m * 256 + c) * 16) = *reinterpret_cast<const uint4*>(row);
+    red[c] = (float)n2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (c < s) red[c] = fmaxf(red[c], red[c + s]);
+        __syncthreads();
+    }
+    if (c == 0) reinterpret_cast<float*>(out + (int64_t)M * tc::kBTileBytes)[m] = red[0];
+    if (!exact || !isfinite((float)n2)) atomicExch(reinterpret_cast<int*>(out + (int64_t)M * tc::kBTileBytes + (int64_t)M * 4), 0);
+}
+
+}  // namespace tc
+
+int64_t encode_tc_prepared_bytes(int d, int M, int C) {
+    const int dm = M > 0 ? d / M : 0;
+    if (C != 256 || !(dm == 2 || dm == 4) || M % tc::kMG) return 0;
+    return (int64_t)M * tc::kBTileBytes + (int64_t)M * 4 + 16;
+}
+
+int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C, void* out, cudaStream_t stream) {
+    if (encode_tc_prepared_bytes(d, M, C) == 0 || !(x_dtype == MILLION_F16 || x_dtype == MILLION_BF16))
+        MILLION_UNSUPPORTED("tensor-core encoder: needs C=256, d/M in {2,4}, M %% 16 == 0, fp16/bf16 input");
+    const int dm = d / M;
+    int one = 1;
+    MILLION_CUDA_OK(cudaMemcpyAsync((char*)out + (int64_t)M * tc::kBTileBytes + (int64_t)M * 4, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
+    unsigned char* o = (unsigned char*)out;
+    if (x_dtype == MILLION_F16) {
+        if (dm == 2) tc::encode_prepare_kernel<__half, 2><<<M, 256, 0, stream>>>(cent, o, M);
+        else tc::encode_prepare_kernel<__half, 4><<<M, 256, 0, stream>>>(cent, o, M);
+    } else {
+        if (dm == 2) tc::encode_prepare_kernel<__nv_bfloat16, 2><<<M, 256, 0, stream>>>(cent, o, M);
+        else tc::encode_prepare_kernel<__nv_bfloat16, 4><<<M, 256, 0, stream>>>(cent, o, M);
+    }
+    MILLION_CUDA_OK(cudaGetLastError());
+    // one-time, synchronous: are the centroids representable in the input format (else the filter bound does not hold)?
+    int flag = 0;
+    MILLION_CUDA_OK(cudaMemcpyAsync(&flag, (char*)out + (int64_t)M * tc::kBTileBytes + (int64_t)M * 4, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MILLION_CUDA_OK(cudaStreamSynchronize(stream));
+    if (!flag) MILLION_UNSUPPORTED("tensor-core encoder: centroids are not exactly representable in the input format");
+    return MILLION_OK;
+}
+
+template <typename T, int DM>
+static int launch_tc_t(const tc::EncArgs& a, cudaStream_t stream) {
+    const size_t smem = tc::kMG * tc::kBTileBytes + 2 * tc::kATileBytes + tc::kZeroBytes + tc::kThreads * 5 * 4 + 16 + 16 + tc::kMG * 4 + 64;
+    static bool configured = false;
+    if (!configured) {
+        MILLION_CUDA_OK(cudaFuncSetAttribute(tc::encode_tc_kernel<T, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int ygroups = a.M / tc::kMG;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    int gx = sms / ygroups;
+    if (gx < 1) gx = 1;
+    if (gx > a.total_tiles) gx = a.total_tiles;
+    dim3 grid(gx, ygroups), block(tc::kThreads);
+    tc::encode_tc_kernel<T, DM><<<grid, block, smem, stream>>>(a);
+    MILLION_CUDA_OK(cudaGetLastError());
+    return MILLION_OK;
+}
+
+int launch_encode_tc(const void* x, int x_dtype, int64_t xhs, const float* cent, const void* prepared, const CodeDst& dst,
+                     int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream, bool probe_only) {
+    if (encode_tc_prepared_bytes(d, M, C) == 0) MILLION_UNSUPPORTED("tensor-core encoder: needs C=256, d/M in {2,4}, M %% 16 == 0");
+    if (!(x_dtype == MILLION_F16 || x_dtype == MILLION_BF16)) MILLION_UNSUPPORTED("tensor-core encoder: fp16/bf16 input only");
+    if (!prepared) MILLION_UNSUPPORTED("tensor-core encoder needs a prepared codebook (million_pq_encoder_prepare)");
+    if (((uintptr_t)x & 15) || ((xhs * 2) & 15) || ((d * 2) & 15)) MILLION_UNSUPPORTED("tensor-core encoder needs 16-byte aligned rows");
+    if (dst.code_bytes != 1) MILLION_UNSUPPORTED("tensor-core encoder writes 1-byte codes");
+    if (probe_only) return MILLION_OK;
+    tc::EncArgs a;
+    a.x = x; a.x_head_stride = xhs; a.prep = (const unsigned char*)prepared; a.cent = cent; a.dst = dst;
+    a.n_heads = n_heads; a.n_tokens = n_tokens; a.d = d; a.M = M;
+    a.tiles_per_head = (n_tokens + tc::kTokTile - 1) / tc::kTokTile;
+    a.total_tiles = a.tiles_per_head * n_heads;
+    const int dm = d / M;
+    if (x_dtype == MILLION_F16) return dm == 2 ? launch_tc_t<__half, 2>(a, stream) : launch_tc_t<__half, 4>(a, stream);
+    return dm == 2 ? launch_tc_t<__nv_bfloat16, 2>(a, stream) : launch_tc_t<__nv_bfloat16, 4>(a, stream);
+}
+
+}  // namespace million

@@ -42,6 +42,32 @@ def _x_view(X):
     return X, hs
 
 
+_enc_prepared = {}
+
+
+def prepare_encoder(cent_f32, x_dtype):
+    """Operand tiles of the tensor-core encoder for (codebook, input dtype); None when the shape is not covered or the
+    centroids are not representable in the input format (then the exact CUDA-core encoder is used)."""
+    if x_dtype not in (torch.float16, torch.bfloat16):
+        return None
+    M, C, dm = cent_f32.shape
+    nbytes = L.lib().million_pq_encoder_prepared_bytes(M * dm, M, C)
+    if nbytes == 0:
+        return None
+    key = (cent_f32.data_ptr(), cent_f32._version, x_dtype, cent_f32.device)
+    if key not in _enc_prepared:
+        if len(_enc_prepared) > 64:
+            _enc_prepared.clear()
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=cent_f32.device)
+        st = L.lib().million_pq_encoder_prepare(_ptr(cent_f32), _DT[x_dtype], M * dm, M, C, _ptr(buf), _stream(cent_f32))
+        if st == L.MILLION_ERR_UNSUPPORTED:
+            buf = None
+        else:
+            L.check(st)
+        _enc_prepared[key] = (buf, cent_f32)
+    return _enc_prepared[key][0]
+
+
 def pq_encode_into(X, cent_f32, codes, *, t0=0, layout="rowmajor", impl=L.IMPL_AUTO):
     """Encode X (bs, nh_k, n, d) and write the codes at token offset t0 of a preallocated cache.
     layout 'rowmajor': codes (bs, nh_k, cap, M); 'transposed': codes (bs, nh_k, M, cap)."""
@@ -58,7 +84,8 @@ def pq_encode_into(X, cent_f32, codes, *, t0=0, layout="rowmajor", impl=L.IMPL_A
         assert codes.shape[0] == bs and codes.shape[1] == nh and codes.shape[2] == M and codes.stride(3) == 1
         hs, ts, ms = codes.stride(1), 1, codes.stride(2)
         assert bs == 1 or codes.stride(0) == nh * codes.stride(1)
-    L.check(L.lib().million_pq_encode(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(codes), codes.element_size(),
+    prep = prepare_encoder(cent_f32, X.dtype) if impl != L.IMPL_GENERIC and codes.element_size() == 1 else None
+    L.check(L.lib().million_pq_encode(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(prep), _ptr(codes), codes.element_size(),
                                       hs, ts, ms, t0, bs * nh, n, d, M, C, impl, _stream(X)))
     return codes
 
@@ -83,7 +110,8 @@ def pq_encode_paged(X, cent_f32, page_pool, page_ids, *, t0, impl=L.IMPL_AUTO):
     assert page_pool.dtype == torch.uint8 and page_pool.is_contiguous() and page_pool.shape[1] == M
     assert page_ids.dtype == torch.int64 and page_ids.is_contiguous() and page_ids.shape[:2] == (bs, nh)
     X, xhs = _x_view(X)
-    L.check(L.lib().million_pq_encode_paged(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(page_pool), _ptr(page_ids),
+    prep = prepare_encoder(cent_f32, X.dtype) if impl != L.IMPL_GENERIC else None
+    L.check(L.lib().million_pq_encode_paged(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(prep), _ptr(page_pool), _ptr(page_ids),
                                             page_ids.shape[2], page_pool.shape[2], t0, bs * nh, n, d, M, C, impl, _stream(X)))
 
 

@@ -63,9 +63,9 @@ def test_argument_errors_are_status_codes(lib):
     assert b"struct_size" in h.million_last_error()
     assert h.million_pq_decode_attn(None, None) == lib.MILLION_ERR_INVALID
     one = ctypes.c_void_p(16)
-    assert h.million_pq_encode(one, 0, 0, one, one, 1, 0, 0, 0, 0, 1, 1, 128, 60, 256, 0, None) == lib.MILLION_ERR_INVALID  # d % M
-    assert h.million_pq_encode(one, 0, 0, one, one, 1, 0, 0, 0, 0, 1, 1, 128, 64, 512, 0, None) == lib.MILLION_ERR_INVALID  # C > 256 in u8
-    assert h.million_pq_encode(None, 0, 0, None, None, 1, 0, 0, 0, 0, 0, 0, 128, 64, 256, 0, None) == lib.MILLION_OK         # empty
+    assert h.million_pq_encode(one, 0, 0, one, None, one, 1, 0, 0, 0, 0, 1, 1, 128, 60, 256, 0, None) == lib.MILLION_ERR_INVALID  # d % M
+    assert h.million_pq_encode(one, 0, 0, one, None, one, 1, 0, 0, 0, 0, 1, 1, 128, 64, 512, 0, None) == lib.MILLION_ERR_INVALID  # C > 256 in u8
+    assert h.million_pq_encode(None, 0, 0, None, None, None, 1, 0, 0, 0, 0, 0, 0, 128, 64, 256, 0, None) == lib.MILLION_OK         # empty
     with pytest.raises(lib.MillionError):
         lib.check(lib.MILLION_ERR_INVALID)
 
