@@ -130,7 +130,8 @@ __device__ __forceinline__ uint32_t gather32(uint32_t r) {
 
 }  // namespace fast
 
-template <typename T, int G>
+// VL = 0: value codes row-major (tokens x 64 bytes); VL = 1: transposed per sub-space (paged pool or (M, ld) rows)
+template <typename T, int G, int VL>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
     using namespace fast;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         unsigned char* pbuf_w = pbuf_p + warp * kTile * 8;
         const uint32_t ks_s = smem_u32(ksp), vs_s = smem_u32(vsp);
         const uint8_t* kbase = a.k_codes + hb * a.k_head_stride;
-        const uint8_t* vbase = a.v_codes + hb * a.v_head_stride;
+        const uint8_t* vbase = a.v_codes + (a.v_layout == MILLION_V_PAGED ? 0 : hb * a.v_head_stride);
 
         // per-lane gather constants
         uint32_t koff[16];   // QK: byte0 = column offset for even b, byte1 = for odd b, bytes 2,3 = 0
@@ -271,8 +272,39 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
             }
             cp_async_commit();
         };
+        // transposed value codes: the tile is 64 sub-space rows of 32 tokens; row m is staged at row pi(m) = m/4 + 16*(m%4)
+        // (32 bytes each) so that the word reads of the PV phase below are bank-conflict free
+        auto issue_vt = [&](int tile) {
+            const int tok0 = t0 + tile * kTile;
+            const bool in_range = tile < n_tiles;
+            const uint8_t* src0 = vbase;
+            int64_t row_stride = a.v_ld;
+            if (in_range) {
+                if (a.v_layout == MILLION_V_PAGED) {
+                    const int64_t page = __ldg(a.v_page_ids + (int64_t)hb * a.n_pages + tok0 / a.page_size);
+                    src0 = a.v_codes + page * 64 * a.page_size + (tok0 % a.page_size);
+                    row_stride = a.page_size;
+                } else {
+                    src0 = vbase + tok0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int chunk = lane + i * 32;            // 0..127: 64 rows * 2 chunks of 16 tokens
+                const int m = chunk >> 1, hc = chunk & 1;
+                int ok = in_range ? (t1 - (tok0 + hc * 16)) : 0;
+                ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
+                const uint32_t dst = vs_s + (uint32_t)((((m >> 2) + 16 * (m & 3)) * 32) + hc * 16);
+                cp_async16(dst, (ok ? src0 : vbase) + (ok ? (int64_t)m * row_stride + hc * 16 : 0), ok);
+            }
+            cp_async_commit();
+        };
+        auto issue_v = [&](int tile) {
+            if constexpr (VL == 0) issue(tile, vbase, vs_s);
+            else issue_vt(tile);
+        };
         issue(warp, kbase, ks_s);
-        issue(warp, vbase, vs_s);
+        issue_v(warp);
 
         __half2 acc[4][G];
 #pragma unroll
@@ -361,27 +393,60 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
             cp_async_wait<1>();          // pending [V(i), K(i+1)] -> V(i) landed
             __syncwarp();
 
-            // ------------------------------------------------ PV: half-warp per token, lane owns 4 sub-spaces
+            // ------------------------------------------------ PV: lane owns 4 sub-spaces (slot k -> 4*lq + ((k + hw) & 3))
+            if constexpr (VL == 0) {
+                // row-major codes: a half-warp per token, the lane's word holds its 4 sub-spaces of that token
 #pragma unroll 4
-            for (int jp = 0; jp < kTile / 2; ++jp) {
-                const int j = 2 * jp + hw;
-                const uint32_t word = lds32(vsp, j * kRowBytes + lq * 4);
-                const uint2 pk = lds64(pbuf_w, j * 8);
-                const __half2 p01 = as_h2(pk.x), p23 = as_h2(pk.y);
+                for (int jp = 0; jp < kTile / 2; ++jp) {
+                    const int j = 2 * jp + hw;
+                    const uint32_t word = lds32(vsp, j * kRowBytes + lq * 4);
+                    const uint2 pk = lds64(pbuf_w, j * 8);
+                    const __half2 p01 = as_h2(pk.x), p23 = as_h2(pk.y);
 #pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    const uint32_t ad = __byte_perm(word, sl < 2 ? voff01 : voff23, vsel[sl]);
-                    const __half2 v = as_h2(gather32<kSmemBase + kVtabOff>(ad));
-                    acc[sl][0] = __hfma2(__low2half2(p01), v, acc[sl][0]);
-                    if constexpr (G >= 2) acc[sl][1] = __hfma2(__high2half2(p01), v, acc[sl][1]);
-                    if constexpr (G == 4) {
-                        acc[sl][2] = __hfma2(__low2half2(p23), v, acc[sl][2]);
-                        acc[sl][3] = __hfma2(__high2half2(p23), v, acc[sl][3]);
+                    for (int sl = 0; sl < 4; ++sl) {
+                        const uint32_t ad = __byte_perm(word, sl < 2 ? voff01 : voff23, vsel[sl]);
+                        const __half2 v = as_h2(gather32<kSmemBase + kVtabOff>(ad));
+                        acc[sl][0] = __hfma2(__low2half2(p01), v, acc[sl][0]);
+                        if constexpr (G >= 2) acc[sl][1] = __hfma2(__high2half2(p01), v, acc[sl][1]);
+                        if constexpr (G == 4) {
+                            acc[sl][2] = __hfma2(__low2half2(p23), v, acc[sl][2]);
+                            acc[sl][3] = __hfma2(__high2half2(p23), v, acc[sl][3]);
+                        }
+                    }
+                }
+            } else {
+                // transposed codes: a word holds 4 tokens of one sub-space.  Half-warp hw takes tokens 16*hw .. 16*hw+15 in
+                // 4 groups of 4; the group order is rotated by lq/4 so the 32 word reads of one instruction hit 32 banks
+                // (staged row pi(m) lies in bank quad 2*(lq%4) + hw, the word inside the chunk is (u + lq/4) % 4).
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int tgl = (u + (lq >> 2)) & 3;                 // token group inside my half
+                    const int tg = tgl + 4 * hw;
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) wv[k] = lds32(vsp, (lq + 16 * ((k + hw) & 3)) * 32 + hw * 16 + tgl * 4);
+                    const uint4 pa = lds128(pbuf_w, tg * 32), pb = lds128(pbuf_w, tg * 32 + 16);
+                    const uint32_t pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t sel = (uint32_t)(4 + (k & 1)) | ((uint32_t)i << 4) | 0x6600u;
+                            const uint32_t ad = __byte_perm(wv[k], k < 2 ? voff01 : voff23, sel);
+                            const __half2 v = as_h2(gather32<kSmemBase + kVtabOff>(ad));
+                            const __half2 p01 = as_h2(pp[2 * i]), p23 = as_h2(pp[2 * i + 1]);
+                            acc[k][0] = __hfma2(__low2half2(p01), v, acc[k][0]);
+                            if constexpr (G >= 2) acc[k][1] = __hfma2(__high2half2(p01), v, acc[k][1]);
+                            if constexpr (G == 4) {
+                                acc[k][2] = __hfma2(__low2half2(p23), v, acc[k][2]);
+                                acc[k][3] = __hfma2(__high2half2(p23), v, acc[k][3]);
+                            }
+                        }
                     }
                 }
             }
             __syncwarp();                                   // every lane is done with the V tile and the p slots
-            issue(tile + kWarps, vbase, vs_s);              // V(i+1) streams in during the next QK phase
+            issue_v(tile + kWarps);                          // V(i+1) streams in during the next QK phase
             if (++since_flush == 2) {                       // packed-half partial sums live for at most 2 tiles (32 terms)
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl)
@@ -509,7 +574,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
-template <typename T, int G>
+template <typename T, int G, int VL>
 static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
     const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + 256;
@@ -518,11 +583,11 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static bool configured = false;
     if (!configured) {
-        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
-    attn_fast_kernel<T, G><<<grid, block, smem, stream>>>(a, prepared, gsub);
+    attn_fast_kernel<T, G, VL><<<grid, block, smem, stream>>>(a, prepared, gsub);
     MILLION_CUDA_OK(cudaGetLastError());
     return MILLION_OK;
 }
@@ -533,15 +598,21 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     const int Gfull = a.nh / a.nh_k;
     if (a.d != 128 || a.M != 64 || a.C != 256) MILLION_UNSUPPORTED("fast decode attention needs d=128, M=64, C=256");
     if (!(Gfull == 1 || Gfull == 2 || Gfull % 4 == 0)) MILLION_UNSUPPORTED("fast decode attention needs nh/nh_k in {1,2,4k}");
-    if (a.v_layout != MILLION_V_ROWMAJOR) MILLION_UNSUPPORTED("fast decode attention: V layout %d not supported yet", a.v_layout);
+    if (a.nk > 0 && a.v_layout == MILLION_V_PAGED && (a.page_size % 32 != 0 || ((uintptr_t)a.v_codes & 15)))
+        MILLION_UNSUPPORTED("fast decode attention: paged V needs page_size %% 32 == 0 and an aligned pool");
+    if (a.nk > 0 && a.v_layout == MILLION_V_TRANSPOSED && ((a.v_ld & 15) || (a.v_head_stride & 15) || ((uintptr_t)a.v_codes & 15)))
+        MILLION_UNSUPPORTED("fast decode attention: transposed V needs 16-byte aligned rows");
     if (!prepared) MILLION_UNSUPPORTED("fast decode attention needs a prepared codebook (million_pq_codebook_prepare)");
-    if (a.nk > 0 && (((uintptr_t)a.k_codes | (uintptr_t)a.v_codes | (uintptr_t)a.k_head_stride | (uintptr_t)a.v_head_stride) & 15))
+    if (a.nk > 0 && (((uintptr_t)a.k_codes | (uintptr_t)a.k_head_stride) & 15))
         MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");
-    if (a.r > 128 || ((uintptr_t)a.k_res & 15)) MILLION_UNSUPPORTED("fast decode attention needs r <= 128 and aligned window");
+    if (a.nk > 0 && a.v_layout == MILLION_V_ROWMAJOR && (((uintptr_t)a.v_codes | (uintptr_t)a.v_head_stride) & 15))
+        MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");
+    if (a.r > 0 && (((uintptr_t)a.k_res | (uintptr_t)a.v_res) & 7)) MILLION_UNSUPPORTED("fast decode attention needs an 8-byte aligned window");
     if (probe_only) return MILLION_OK;
     const int G = Gfull >= 4 ? 4 : Gfull, gsub = Gfull >= 4 ? Gfull / 4 : 1;
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
-#define MILLION_FAST_CASE(TT, GG) return launch_fast_t<TT, GG>(a, prep, gsub, stream)
+#define MILLION_FAST_CASE(TT, GG) \
+    return a.v_layout == MILLION_V_ROWMAJOR ? launch_fast_t<TT, GG, 0>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1>(a, prep, gsub, stream)
     if (io_dtype == MILLION_F16) {
         if (G == 4) MILLION_FAST_CASE(__half, 4);
         if (G == 2) MILLION_FAST_CASE(__half, 2);

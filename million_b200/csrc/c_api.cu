@@ -204,8 +204,8 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     a.res_len = p->res_len; a.v_layout = p->v_layout; a.page_size = p->page_size; a.n_pages = p->n_pages;
     a.n_splits = S;
     const int units = (p->nk + 15) / 16;
-    a.units_per_split = (units + S - 1) / S;
-    if (a.units_per_split < 1) a.units_per_split = 1;
+    a.units_per_split = ((units + S - 1) / S + 3) / 4 * 4;   // splits start on multiples of 64 tokens (tiles never straddle a page)
+    if (a.units_per_split < 4) a.units_per_split = 4;
     MILLION_REQUIRE(S + 1 <= 1024, "attn: at most 1023 splits");
     a.scale_log2 = kLog2e / sqrtf((float)p->d);
     a.dbg_timing = g_dbg_timing;

@@ -144,18 +144,24 @@ __device__ __forceinline__ float exact_dist(const float (&xv)[DM], const float* 
     return acc;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Two warpgroups (4 warps = 128 threads = the 128 token rows of a tile) work on alternating items, each with its own
+// A slot, TMEM buffer (256 columns) and mbarrier: while one group waits for its MMA the other one is in its epilogue.
 template <typename T, int DM>
 __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* Bs = smem;                                   // kMG * 4 KB
-    unsigned char* As = Bs + kMG * kBTileBytes;                 // 2 slots * 2 KB
+    unsigned char* As = Bs + kMG * kBTileBytes;                 // 2 slots * 2 KB (one per warpgroup)
     unsigned char* Zs = As + 2 * kATileBytes;                   // 4 KB of zeros (second K chunk of both operands)
-    float* xch = reinterpret_cast<float*>(Zs + kZeroBytes);     // 256 threads * 5 words
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kThreads * 5);   // 2 mbarriers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Zs + kZeroBytes);   // 2 mbarriers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     float* cmax_s = reinterpret_cast<float*>(tmem_slot + 2);    // kMG floats
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wg = warp >> 2, row = tid & 127;                  // warpgroup, token row inside the tile
     const int m0 = blockIdx.y * kMG;
     constexpr uint32_t kOne = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
     constexpr uint32_t kFmt = std::is_same<T, __half>::value ? 0u : 1u;
@@ -183,150 +189,97 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t zs = smem_u32(Zs);
+    const uint32_t as = smem_u32(As + wg * kATileBytes);
+    const uint32_t bar = smem_u32(&bars[wg]);
+    const uint32_t dcol = tmem_base + wg * 256;
+    const uint32_t taddr = dcol + ((uint32_t)((warp & 3) * 32) << 16);   // my TMEM lane quarter
 
-    // my TMEM view: lanes 32*(warp%4) .., columns 128*(warp/4) .. of the active buffer
-    const int q = warp & 3, half = warp >> 2;
-    const int row = q * 32 + lane;              // token row inside the tile handled by this thread (both halves)
-
-    auto issue_mma = [&](int slot, int j) {
-        const uint32_t as = smem_u32(As + slot * kATileBytes), bs = smem_u32(Bs + j * kBTileBytes);
-        umma_f16(tmem_base + slot * 256, make_desc(as, zs - as, 128), make_desc(bs, zs - bs, 128), idesc);
-        umma_commit(smem_u32(&bars[slot]));
-    };
-
-    uint32_t it = 0;                            // running item counter of this CTA (slot = it & 1, parity = (it >> 1) & 1)
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    // items of this CTA: (tile, j) for tile = blockIdx.x, += gridDim.x and j < kMG; warpgroup wg takes every other one
+    const int n_my_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_items = n_my_tiles * kMG;
+    uint32_t phase = 0;
+    for (int item = wg; item < n_items; item += 2) {
+        const int tile = blockIdx.x + (item / kMG) * gridDim.x, j = item % kMG;
         const int head = tile / a.tiles_per_head;
         const int tok = (tile % a.tiles_per_head) * kTokTile + row;
         const bool live = tok < a.n_tokens;
-        // my token's values for the kMG sub-spaces of this CTA: kMG * DM halves
-        uint32_t xr[kMG * DM / 2];
+
+        // ---- A row of my token for sub-space m0 + j, |x_m|^2
+        uint32_t xw[DM / 2];
         {
-            const T* xp = reinterpret_cast<const T*>(a.x) + head * a.x_head_stride + (int64_t)(live ? tok : 0) * a.d + m0 * DM;
-            const uint4* xp4 = reinterpret_cast<const uint4*>(xp);
+            const uint32_t* xp = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(a.x) + head * a.x_head_stride +
+                                                                   (int64_t)(live ? tok : 0) * a.d + (m0 + j) * DM);
 #pragma unroll
-            for (int i = 0; i < kMG * DM / 8; ++i) {
-                uint4 v = live ? __ldg(xp4 + i) : make_uint4(0, 0, 0, 0);
-                xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
-            }
+            for (int i = 0; i < DM / 2; ++i) xw[i] = live ? __ldg(xp + i) : 0u;
         }
-        auto build_A = [&](int slot, int j) {
-            if (half == 0) {   // one writer per token row
-                uint4 rowv;
-                if constexpr (DM == 2) rowv = make_uint4(xr[j], kOne | (kOne << 16), kOne, 0u);
-                else rowv = make_uint4(xr[2 * j], xr[2 * j + 1], kOne | (kOne << 16), kOne);
-                *reinterpret_cast<uint4*>(As + slot * kATileBytes + row * 16) = rowv;
-            }
-        };
-        uint32_t codes[kMG / 4] = {0, 0, 0, 0};
-
-        // ---- software pipeline over the kMG items of this tile (the pipeline drains at the end of every tile)
-        build_A(it & 1, 0);
+        uint4 rowv;
+        if constexpr (DM == 2) rowv = make_uint4(xw[0], kOne | (kOne << 16), kOne, 0u);
+        else rowv = make_uint4(xw[0], xw[1], kOne | (kOne << 16), kOne);
+        *reinterpret_cast<uint4*>(As + wg * kATileBytes + row * 16) = rowv;
         fence_async_proxy();
-        tc_fence_before();
-        __syncthreads();
+        tc_fence_before();                       // my tcgen05.ld of the previous item are done (wait::ld) and ordered
+        named_bar_sync(1 + wg, 128);
         tc_fence_after();
-        if (tid == 0) issue_mma(it & 1, 0);
-
+        if (row == 0) {
+            const uint32_t bs = smem_u32(Bs + j * kBTileBytes);
+            umma_f16(dcol, make_desc(as, zs - as, 128), make_desc(bs, zs - bs, 128), idesc);
+            umma_commit(bar);
+        }
+        float xv[DM];
+        {
+            const float2 f0 = io<T>::to_f2(xw[0]);
+            xv[0] = f0.x; xv[1] = f0.y;
+            if constexpr (DM == 4) { const float2 f1 = io<T>::to_f2(xw[1]); xv[2] = f1.x; xv[3] = f1.y; }
+        }
+        float x2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < kMG; ++j, ++it) {
-            const int slot = it & 1;
-            if (j + 1 < kMG) {
-                // the other slot/buffer is free: MMA(it-1) was waited for and its D was read before the last barrier
-                build_A(slot ^ 1, j + 1);
-                fence_async_proxy();
-                tc_fence_before();
-                __syncthreads();
-                tc_fence_after();
-                if (tid == 0) issue_mma(slot ^ 1, j + 1);
-            }
-            mbar_wait(smem_u32(&bars[slot]), (it >> 1) & 1);
-            tc_fence_after();
+        for (int k = 0; k < DM; ++k) x2 = fmaf(xv[k], xv[k], x2);
+        const float eps = (x2 + cmax_s[j]) * kEpsScale;
 
-            // |x_m|^2 and the filter width
-            float xv[DM];
-            if constexpr (DM == 2) {
-                const float2 f = io<T>::to_f2(xr[j]);
-                xv[0] = f.x; xv[1] = f.y;
-            } else {
-                const float2 f0 = io<T>::to_f2(xr[2 * j]), f1 = io<T>::to_f2(xr[2 * j + 1]);
-                xv[0] = f0.x; xv[1] = f0.y; xv[2] = f1.x; xv[3] = f1.y;
-            }
-            float x2 = 0.f;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+
+        // ---- epilogue: the 256 distances of my row, four chunks of 64 columns
+        uint32_t cw[8];
+        float mn[4];
+        float best = INFINITY;
 #pragma unroll
-            for (int k = 0; k < DM; ++k) x2 = fmaf(xv[k], xv[k], x2);
-            const float eps = (x2 + cmax_s[j]) * kEpsScale;
-
-            // ---- epilogue: 128 columns of my row, two chunks of 64
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + half * 128;
+        for (int ch = 0; ch < 4; ++ch) {
             float v[64];
-            uint32_t w[4];
-            tmem_ld64(taddr, v);
-            const float mn0 = reduce_chunk(v, INFINITY, eps, w[0], w[1]);
-            tmem_ld64(taddr + 64, v);
-            const float mn1 = reduce_chunk(v, mn0, eps, w[2], w[3]);
-            tc_fence_before();
-            const float mh = fminf(mn0, mn1);
-            if (mn0 > mh + eps) { w[0] = 0; w[1] = 0; }     // chunk 0 was filtered against a looser threshold
-            float* me = xch + tid * 5;
-            me[0] = mh;
-            me[1] = __uint_as_float(w[0]); me[2] = __uint_as_float(w[1]); me[3] = __uint_as_float(w[2]); me[4] = __uint_as_float(w[3]);
-            __syncthreads();
-            if (half == 0) {
-                const float* other = xch + (tid + 128) * 5;
-                const float mo = other[0];
-                const float mstar = fminf(mh, mo);
-                uint32_t cw[8];
-                const bool keep0 = !(mh > mstar + eps), keep1 = !(mo > mstar + eps);
+            tmem_ld64(taddr + ch * 64, v);
+            mn[ch] = reduce_chunk(v, best, eps, cw[2 * ch], cw[2 * ch + 1]);
+            best = fminf(best, mn[ch]);
+        }
+        int cnt = 0, code = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    cw[i] = keep0 ? w[i] : 0u;
-                    cw[4 + i] = keep1 ? __float_as_uint(other[1 + i]) : 0u;
+        for (int ch = 3; ch >= 0; --ch) {
+            if (mn[ch] > best + eps) { cw[2 * ch] = 0; cw[2 * ch + 1] = 0; }     // filtered against a looser threshold
+            cnt += __popc(cw[2 * ch]) + __popc(cw[2 * ch + 1]);
+            if (cw[2 * ch + 1]) code = 64 * ch + 32 + __clz(cw[2 * ch + 1]);
+            if (cw[2 * ch]) code = 64 * ch + __clz(cw[2 * ch]);                  // lowest candidate column wins
+        }
+        if (cnt != 1 && live) {
+            // rare: several centroids inside the filter width (or a degenerate all-zero row): exact fp32 arg-min
+            const float* cm = a.cent + (int64_t)(m0 + j) * 256 * DM;
+            float bestd = INFINITY;
+            int bi = 0;
+            for (int i = 0; i < 8; ++i) {
+                uint32_t bits = cnt == 0 ? 0xffffffffu : cw[i];
+                while (bits) {
+                    const int lz = __clz(bits);
+                    bits &= ~(0x80000000u >> lz);
+                    const int c = 32 * i + lz;
+                    float cv[DM];
+#pragma unroll
+                    for (int k = 0; k < DM; ++k) cv[k] = __ldg(cm + c * DM + k);
+                    const float dd = exact_dist<DM>(xv, cv);
+                    if (dd < bestd) { bestd = dd; bi = c; }
                 }
-                int cnt = 0, code = 0;
-#pragma unroll
-                for (int i = 7; i >= 0; --i) {
-                    cnt += __popc(cw[i]);
-                    if (cw[i]) code = 32 * i + __clz(cw[i]);      // lowest candidate column
-                }
-                if (cnt != 1 && live) {
-                    // rare: several centroids inside the filter width (or a degenerate all-zero row): exact fp32 arg-min
-                    const float* cm = a.cent + (int64_t)(m0 + j) * 256 * DM;
-                    float best = INFINITY;
-                    int bi = 0;
-                    if (cnt == 0) {
-                        for (int c = 0; c < 256; ++c) {
-                            float cv[DM];
-#pragma unroll
-                            for (int k = 0; k < DM; ++k) cv[k] = __ldg(cm + c * DM + k);
-                            const float dd = exact_dist<DM>(xv, cv);
-                            if (dd < best) { best = dd; bi = c; }
-                        }
-                    } else {
-                        for (int i = 0; i < 8; ++i) {
-                            uint32_t bits = cw[i];
-                            while (bits) {
-                                const int lz = __clz(bits);
-                                bits &= ~(0x80000000u >> lz);
-                                const int c = 32 * i + lz;
-                                float cv[DM];
-#pragma unroll
-                                for (int k = 0; k < DM; ++k) cv[k] = __ldg(cm + c * DM + k);
-                                const float dd = exact_dist<DM>(xv, cv);
-                                if (dd < best) { best = dd; bi = c; }
-                            }
-                        }
-                    }
-                    code = bi;
-                }
-                codes[j >> 2] |= (uint32_t)code << (8 * (j & 3));
             }
+            code = bi;
         }
-        // ---- store the kMG codes of my token
-        if (half == 0 && live) {
-#pragma unroll
-            for (int j = 0; j < kMG; ++j) a.dst.put(head, tok, m0 + j, (codes[j >> 2] >> (8 * (j & 3))) & 0xff);
-        }
+        if (live) a.dst.put(head, tok, m0 + j, code);
     }
 
     tc_fence_before();
@@ -404,7 +357,7 @@ int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C
 
 template <typename T, int DM>
 static int launch_tc_t(const tc::EncArgs& a, cudaStream_t stream) {
-    const size_t smem = tc::kMG * tc::kBTileBytes + 2 * tc::kATileBytes + tc::kZeroBytes + tc::kThreads * 5 * 4 + 16 + 16 + tc::kMG * 4 + 64;
+    const size_t smem = tc::kMG * tc::kBTileBytes + 2 * tc::kATileBytes + tc::kZeroBytes + 16 + 16 + tc::kMG * 4 + 64;
     static bool configured = false;
     if (!configured) {
         MILLION_CUDA_OK(cudaFuncSetAttribute(tc::encode_tc_kernel<T, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

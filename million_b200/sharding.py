@@ -1,0 +1,61 @@
+"""Multi-GPU partitioning of the PQ decode-attention path (one process per GPU, torch.distributed).
+
+The reference is single-GPU (scripts/modeldb/main_pq.py:74 "TODO: support multi-gpu"); the path shards in two ways:
+
+  * by KV head — codes, windows, block tables are independent per (batch, kv-head): rank g owns kv-heads
+    [g*nh_k/G, (g+1)*nh_k/G) and their query heads.  No collective on the data path.
+  * by sequence (split-KV) for batch-1 long contexts — rank g owns a page-aligned token range, computes the
+    un-normalised (o, m, l) state of its range with the same kernel (MILLION_ATTN_PARTIAL_ONLY), the states are
+    all-gathered (bs*nh*(d+2) fp32 = 16.6 KB per rank for Llama-3.1-8B shapes) over NCCL/NVLink and merged with the
+    log-sum-exp algebra of flash_decoding_reduce_kernel (scripts/modeldb/bindings/Kernel.cuh:1249-1269).
+    The fp16 window lives on the last rank.
+"""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def kv_head_shard(nh: int, nh_k: int, world: int, rank: int) -> Tuple[range, range]:
+    """(kv-head range, query-head range) owned by `rank`.  nh_k must be divisible by world."""
+    if nh_k % world:
+        raise ValueError(f"num_key_value_heads={nh_k} is not divisible by world size {world}")
+    per = nh_k // world
+    G = nh // nh_k
+    return range(rank * per, (rank + 1) * per), range(rank * per * G, (rank + 1) * per * G)
+
+
+def split_kv_ranges(nk: int, world: int, page: int = 64) -> List[Tuple[int, int]]:
+    """Page-aligned token ranges [(start, end)] of the nk quantized tokens, one per rank, sizes differ by <= 1 page."""
+    n_pages = (nk + page - 1) // page
+    base, extra = divmod(n_pages, world)
+    out, p = [], 0
+    for g in range(world):
+        q = base + (1 if g < extra else 0)
+        out.append((min(p * page, nk), min((p + q) * page, nk)))
+        p += q
+    return out
+
+
+def allgather_partials(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """partial (rows, d+2) fp32 -> (world, rows, d+2): one small all-gather (NCCL over NVLink on GPUs, gloo on CPU)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(partial.shape), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out.view(-1), partial.contiguous().view(-1), group=group)
+    return out
+
+
+def splitkv_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, group=None, merge_fn=None,
+                        attn_fn=None, **attn_kw):
+    """Split-KV decode attention across the ranks of `group`.
+
+    Every rank passes its LOCAL slice of the code caches; `r_local` is the window length on this rank (non-zero on one
+    rank only).  Returns the full (bs, nh, 1, d) output on every rank."""
+    from . import ops
+    attn_fn = attn_fn or ops.pq_decode_attn
+    merge_fn = merge_fn or ops.lse_merge
+    bs, nh, d = q.shape[0], q.shape[1], q.shape[-1]
+    partial = torch.empty(bs * nh, d + 2, dtype=torch.float32, device=q.device)
+    attn_fn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, partial=partial, **attn_kw)
+    parts = allgather_partials(partial, group)
+    return merge_fn(parts, d, q.dtype).view(bs, nh, 1, d)
