@@ -187,6 +187,35 @@ def time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=0):
     return graph, layers, (kcent, vcent)
 
 
+def encode_rate(torch, ops, device):
+    """PQ encode throughput on Llama-3.1-8B prefill shapes: K of one layer = 8 kv-heads x 32768 tokens (tcgen05 encoder)."""
+    n = 32768
+    X = torch.randn(1, NH_K, n, D, device=device).half()
+    cent = torch.randn(M, C, D // M, device=device).half().float().contiguous()
+    codes = torch.empty(1, NH_K, n, M, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        ops.pq_encode_into(X, cent, codes)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(10):
+        ops.pq_encode_into(X, cent, codes)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    vec_per_s = NH_K * n / (ms * 1e-3)
+    return {"M_head_vectors_per_s": vec_per_s / 1e6, "Mtok_per_s_32_layers_K_and_V": vec_per_s / (2 * NH_K * LAYERS) / 1e6,
+            "algorithmic_TFLOPs": vec_per_s * 2 * D * C / 1e12, "ms_per_layer_K_32k": ms}
+
+
+def ncu_traffic(bs):
+    """dram bytes per launch from the committed ncu capture of this kernel (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        j = json.load(open(p)).get(f"attn_fast_bs{bs}")
+        if j:
+            return j["dram_bytes_read"] + j["dram_bytes_write"]
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -263,6 +292,10 @@ def main():
         a1 = algorithmic_bytes(1, nk, r) / (s1 / launches) / 1e9
         extra["bs1"] = {"tokens_per_s": steps / s1, "us_per_layer": s1 / launches * 1e6, "achieved_GBps": a1, "frac": a1 / peak}
         del g1, l1, c1
+        try:
+            extra["encode"] = encode_rate(torch, ops, device)
+        except Exception as e:
+            extra["encode"] = {"error": repr(e)}
     barrier()
 
     # ---- end-to-end through the reference-facing API with HOST buffers
@@ -313,7 +346,7 @@ def main():
             "config": {"workload": f"llama31-8b-shapes_pq4bit_decode_attn_ctx{args.ctx}", "bs_per_gpu": bs, "layers": LAYERS, "nh": NH, "nh_k": NH_K,
                        "d": D, "M": M, "C": C, "window": r, "sharding": "independent sequences per rank (no collective)" if world > 1 else "single GPU",
                        "l2": f"inputs larger than L2: {LAYERS} layer caches, {LAYERS * alg / 1e9:.2f} GB touched per step", "kernel": args.kernel},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(bs),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "us_per_launch": per_launch * 1e6},
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "DynamicPQCache.decoding x 32 layers, pinned host q/k/v in, host out"},
