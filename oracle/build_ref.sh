@@ -15,7 +15,7 @@ PY
 )
 TORCH_LIB=$($PY -c "import torch, os; print(os.path.join(os.path.dirname(torch.__file__), 'lib'))")
 PY_INC=$($PY -c "import sysconfig; print(sysconfig.get_paths()['include'])")
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 --use_fast_math -ftz=true -std=c++17 -shared -Xcompiler -fPIC \
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 --use_fast_math -ftz=true -std=c++17 --expt-relaxed-constexpr -shared -Xcompiler -fPIC \
   -I "$REFERENCE/scripts/modeldb/bindings" $TORCH_INC -I "$PY_INC" -D_GLIBCXX_USE_CXX11_ABI=1 \
   -L "$TORCH_LIB" -lc10 -ltorch_cpu -Xlinker -rpath -Xlinker "$TORCH_LIB" \
   -o "$OUT/libref_kernels.so" "$HERE/ref_kernels_wrapper.cu"
