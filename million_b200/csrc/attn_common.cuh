@@ -128,19 +128,19 @@ __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, fl
 }
 
 // Arrival ticket: returns true in every thread of the LAST CTA of group `grp` (of `expected` CTAs).
+// The block's partial-state writes are ordered before the ticket by bar.sync + an acq_rel RMW at gpu scope (cheaper than a
+// full __threadfence in every thread); the last CTA's loads (ld.cg after the second bar.sync) observe all of them.
 __device__ __forceinline__ bool last_cta_of_group(int* counters, int grp, int expected, int* smem_flag) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int t = atomicAdd(counters + grp, 1);
+        int t;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(counters + grp) : "memory");
         const int last = (t == expected - 1);
         if (last) counters[grp] = 0;  // leave the counter clean for the next launch
         *smem_flag = last;
     }
     __syncthreads();
-    const bool last = (*smem_flag != 0);
-    if (last) __threadfence();
-    return last;
+    return *smem_flag != 0;
 }
 
 }  // namespace million

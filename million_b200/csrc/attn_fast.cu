@@ -23,13 +23,11 @@ namespace million {
 
 namespace fast {
 
-constexpr int kPairs = 8;                       // (QK warp, PV warp) pairs
-constexpr int kWarps = 2 * kPairs;
+constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kTile = 32;                       // tokens per tile
+constexpr int kTile = 32;                       // tokens per warp tile
 constexpr int kRowBytes = 64;                   // M = 64 one-byte codes
-constexpr int kTileBytes = kTile * kRowBytes;   // 2 KB: one K tile per QK warp, one V tile per PV warp
-constexpr int kPSlot = kTile * 8 + 32;          // 4 halves per token + the rescale factors of the tile
+constexpr int kStageBytes = 2 * kTile * kRowBytes;   // one K tile + one V tile per warp
 constexpr int kVtabBytes = 64 * 1024;
 constexpr float kRescaleMargin = 6.f;           // log2 units: p <= 64 before a rescale is forced
 
@@ -48,22 +46,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "MB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni MB_DONE;\n\t"
-        "bra.uni MB_WAIT;\n\t"
-        "MB_DONE:\n\t}"
-        ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -111,6 +93,24 @@ int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, 
 // ------------------------------------------------------------------------------------------------
 namespace fast {
 
+// Per-warp online-softmax state (uniform across the lanes of the warp) and accumulators.
+template <int G>
+struct WarpState {
+    float m[G];          // running max, log2 units (scaled logits)
+    float l[G];          // per-LANE partial denominator (summed across lanes at the end)
+    float o[4][G][2];    // per-lane fp32 output accumulators: slot s -> sub-space 4*l' + ((s + hw) & 3), 2 dims
+};
+
+template <int G>
+__device__ __forceinline__ void state_init(WarpState<G>& st) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) { st.m[g] = -INFINITY; st.l[g] = 0.f; }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) { st.o[b][g][0] = 0.f; st.o[b][g][1] = 0.f; }
+}
+
 // Table gathers with an absolute shared-window address: the PRMT result (code << 8 | column offset) is the register part,
 // the table base is an immediate, so a gather is exactly PRMT + LDS.  Not volatile: the tables are read-only in the main
 // loop and the compiler may schedule these loads freely.  kSmemBase is checked at kernel entry.
@@ -131,26 +131,21 @@ __device__ __forceinline__ uint32_t gather32(uint32_t r) {
 }  // namespace fast
 
 // VL = 0: value codes row-major (tokens x 64 bytes); VL = 1: transposed per sub-space (paged pool or (M, ld) rows)
-//
-// 16 warps = 8 pairs.  In pair p the QK warp (warp p) scores the tokens of tile p, p+8, ... and hands the probabilities to
-// the PV warp (warp 8+p) through a 288-byte shared slot guarded by two mbarriers (full / empty), so the LUT-gather phase
-// of one tile overlaps the value-gather phase of the previous one and four warps share every scheduler.
 template <typename T, int G, int VL>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
     using namespace fast;
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr uint32_t kLutOff = 0, kVtabOff = LutCfg<G>::bytes, kStageOff = kVtabOff + kVtabBytes;   // stage = K tiles then V tiles
-    constexpr uint32_t kPbufOff = kStageOff + 2 * kPairs * kTileBytes, kBarOff = kPbufOff + kPairs * kPSlot, kMiscOff = kBarOff + kPairs * 16;
+    constexpr uint32_t kLutOff = 0, kVtabOff = LutCfg<G>::bytes, kStageOff = kVtabOff + kVtabBytes;
+    constexpr uint32_t kPbufOff = kStageOff + kWarps * kStageBytes, kMiscOff = kPbufOff + kWarps * kTile * 8;
     unsigned char* lut_p = smem + kLutOff;
-    unsigned char* stage_p = smem + kStageOff;
-    unsigned char* pbuf_p = smem + kPbufOff;
+    unsigned char* stage_p = smem + kStageOff;                           // kWarps * (K tile + V tile)
+    unsigned char* pbuf_p = smem + kPbufOff;                             // kWarps * kTile * 8 bytes (4 halves per token)
     int* flag = reinterpret_cast<int*>(smem + kMiscOff);
+    float* red = reinterpret_cast<float*>(smem + kMiscOff + 16);         // 33 floats
     // after the main loop the stage buffers and p slots are dead: reuse them for the cross-warp combine and the merge
-    float* xch = reinterpret_cast<float*>(stage_p);                      // 2 * kPairs entries of kEntry floats, then kMergeScratch
+    float* xch = reinterpret_cast<float*>(stage_p);                      // 2 * kWarps * G * 130 floats, then kMergeScratch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_qk = warp < kPairs;
-    const int pair = warp & (kPairs - 1);
     if (smem_u32(smem) != kSmemBase) {
         if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
             printf("million_b200: dynamic shared memory starts at 0x%x, expected 0x%x\n", smem_u32(smem), kSmemBase);
@@ -166,11 +161,6 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     int t0, t1;
     split_range(a, split, t0, t1);
     const bool has_codes = t1 > t0;
-    const uint32_t bar_full = smem_u32(smem + kBarOff + pair * 16), bar_empty = bar_full + 8;
-    if (tid < kPairs) {
-        mbar_init(smem_u32(smem + kBarOff + tid * 16), 1);
-        mbar_init(smem_u32(smem + kBarOff + tid * 16 + 8), 1);
-    }
 
     // ---------------------------------------------------------------- prologue: V table + K LUT
     if (has_codes) {
@@ -208,6 +198,8 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
             else cp_async_wait<0>();
             __syncthreads();
             const unsigned char* src = stage_p + (ch & 1) * 16384;
+            // fp32 products of exact fp16 operands, rounded once to fp16 (a packed-half build is 0.7 us faster per CTA but
+            // costs a second rounding, visible on peaked score distributions)
 #pragma unroll 4
             for (int cl = tid >> 6; cl < 64; cl += kThreads / 64) {
                 const int c = ch * 64 + cl;
@@ -232,51 +224,104 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     __syncthreads();
     dbg_stamp(a, 1);
 
-    // ---------------------------------------------------------------- main loop
-    const int lq = lane & 15, hw = lane >> 4;
-    const int n_tiles = has_codes ? (t1 - t0 + kTile - 1) / kTile : 0;
-    unsigned char* pslot = pbuf_p + pair * kPSlot;
-    // QK-warp state: running max (uniform) and per-lane partial denominators.  PV-warp state: output accumulators,
-    // slot s of lane (hw, lq) = sub-space 4*lq + ((s + hw) & 3), 2 dims.
-    float run_m[G], run_l[G], out_o[4][G][2];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        run_m[g] = -INFINITY; run_l[g] = 0.f;
-#pragma unroll
-        for (int sl = 0; sl < 4; ++sl) { out_o[sl][g][0] = 0.f; out_o[sl][g][1] = 0.f; }
-    }
+    // ---------------------------------------------------------------- main loop over this warp's tiles
+    WarpState<G> st;
+    state_init(st);
 
-    if (has_codes && is_qk) {
-        // ================================================================ QK warp
+    if (has_codes) {
+        const int lq = lane & 15, hw = lane >> 4;
         const int rot = (lq + hw) & 15;
-        unsigned char* ksp = stage_p + pair * kTileBytes;
-        const uint32_t ks_s = smem_u32(ksp);
+        unsigned char* ksp = stage_p + warp * kStageBytes;
+        unsigned char* vsp = ksp + kTile * kRowBytes;
+        unsigned char* pbuf_w = pbuf_p + warp * kTile * 8;
+        const uint32_t ks_s = smem_u32(ksp), vs_s = smem_u32(vsp);
         const uint8_t* kbase = a.k_codes + hb * a.k_head_stride;
-        uint32_t koff[16];   // byte0 = column offset for even b, byte1 = for odd b, bytes 2,3 = 0
+        const uint8_t* vbase = a.v_codes + (a.v_layout == MILLION_V_PAGED ? 0 : hb * a.v_head_stride);
+
+        // per-lane gather constants
+        uint32_t koff[16];   // QK: byte0 = column offset for even b, byte1 = for odd b, bytes 2,3 = 0
 #pragma unroll
         for (int w = 0; w < 16; ++w) {
             const int Wl = (w + rot) & 15;
             if constexpr (G == 4) koff[w] = (uint32_t)(Wl * 8) | ((uint32_t)(Wl * 8 + 128) << 8);
             else koff[w] = (uint32_t)(Wl * 4) | ((uint32_t)(Wl * 4 + 64) << 8);   // + (bb>>1)*128 comes from the immediate
         }
-        auto issue_k = [&](int tile) {
+        // PV: slot s -> byte bb = (s + hw) & 3 of the lane's V code word; column offset col_of(4*lq + bb) * 4
+        uint32_t voff01, voff23, vsel[4];
+        {
+            uint32_t o[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int bb = (s + hw) & 3;
+                o[s] = (uint32_t)(col_of(4 * lq + bb) * 4);
+                // result = [off (from voff, byte 4 + (s&1)), code (byte bb of the word), 0, 0]
+                vsel[s] = (uint32_t)(4 + (s & 1)) | ((uint32_t)bb << 4) | (6u << 8) | (6u << 12);
+            }
+            voff01 = o[0] | (o[1] << 8);
+            voff23 = o[2] | (o[3] << 8);
+        }
+
+        const int n_tiles = (t1 - t0 + kTile - 1) / kTile;
+        // one K buffer and one V buffer per warp; K(i+1) is requested right after QK(i), V(i+1) right after PV(i)
+        auto issue = [&](int tile, const uint8_t* gbase, uint32_t dst) {
             const int tok0 = t0 + tile * kTile;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int chunk = lane + i * 32;            // 0..127: 32 tokens * 4 chunks of 16 B
                 const int tok = tok0 + (chunk >> 2);
                 const int ok = (tile < n_tiles && tok < t1) ? 16 : 0;
-                cp_async16(ks_s + chunk * 16, kbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
+                cp_async16(dst + chunk * 16, gbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
             }
             cp_async_commit();
         };
-        issue_k(pair);
-        int n = 0;
-        for (int tile = pair; tile < n_tiles; tile += kPairs, ++n) {
-            cp_async_wait<0>();
+        // transposed value codes: the tile is 64 sub-space rows of 32 tokens; row m is staged at row pi(m) = m/4 + 16*(m%4)
+        // (32 bytes each) so that the word reads of the PV phase below are bank-conflict free
+        auto issue_vt = [&](int tile) {
+            const int tok0 = t0 + tile * kTile;
+            const bool in_range = tile < n_tiles;
+            const uint8_t* src0 = vbase;
+            int64_t row_stride = a.v_ld;
+            if (in_range) {
+                if (a.v_layout == MILLION_V_PAGED) {
+                    const int64_t page = __ldg(a.v_page_ids + (int64_t)hb * a.n_pages + tok0 / a.page_size);
+                    src0 = a.v_codes + page * 64 * a.page_size + (tok0 % a.page_size);
+                    row_stride = a.page_size;
+                } else {
+                    src0 = vbase + tok0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int chunk = lane + i * 32;            // 0..127: 64 rows * 2 chunks of 16 tokens
+                const int m = chunk >> 1, hc = chunk & 1;
+                int ok = in_range ? (t1 - (tok0 + hc * 16)) : 0;
+                ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
+                const uint32_t dst = vs_s + (uint32_t)((((m >> 2) + 16 * (m & 3)) * 32) + hc * 16);
+                cp_async16(dst, (ok ? src0 : vbase) + (ok ? (int64_t)m * row_stride + hc * 16 : 0), ok);
+            }
+            cp_async_commit();
+        };
+        auto issue_v = [&](int tile) {
+            if constexpr (VL == 0) issue(tile, vbase, vs_s);
+            else issue_vt(tile);
+        };
+        issue(warp, kbase, ks_s);
+        issue_v(warp);
+
+        __half2 acc[4][G];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[sl][g] = __float2half2_rn(0.f);
+        int since_flush = 0;
+
+        for (int tile = warp; tile < n_tiles; tile += kWarps) {
+            cp_async_wait<1>();          // pending [K(i), V(i)] -> K(i) landed
             __syncwarp();
             const int tok = t0 + tile * kTile + lane;
             const bool valid = tok < t1;
+
+            // ------------------------------------------------ QK: 64 conflict-free LUT gathers for my token
             float s[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) s[g] = 0.f;
@@ -287,14 +332,15 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
             for (int w = 0; w < 16; ++w) {
 #pragma unroll
                 for (int bq = 0; bq < 4; ++bq) {
-                    constexpr uint32_t selc[4] = {0x6604u, 0x6615u, 0x6624u, 0x6635u};
                     if constexpr (G == 4) {
+                        constexpr uint32_t selc[4] = {0x6604u, 0x6615u, 0x6624u, 0x6635u};
                         const uint32_t ad = __byte_perm(words[w], koff[w], selc[bq]);     // (code << 8) | column offset
                         const uint2 e = (bq >> 1) ? gather64<kSmemBase + kLutOff + 65536>(ad) : gather64<kSmemBase + kLutOff>(ad);
                         fhadd2(s[0], s[1], e.x);
                         fhadd2(s[2], s[3], e.y);
                     } else {
                         // the two half-warps use different bytes in the same step so that all 32 lanes hit 32 banks
+                        constexpr uint32_t selc[4] = {0x6604u, 0x6615u, 0x6624u, 0x6635u};
                         const int b1 = (bq + 1) & 3;
                         const uint32_t ad = __byte_perm(words[w], koff[w], hw ? selc[b1] : selc[bq]) + (uint32_t)(((hw ? b1 : bq) >> 1) * 128);
                         const uint32_t e = gather32<kSmemBase + kLutOff>(ad);
@@ -304,137 +350,59 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
                 }
             }
             __syncwarp();                                   // every lane has read its K row
-            issue_k(tile + kPairs);                         // K(n+1) streams in while the tail of this tile is processed
+            issue(tile + kWarps, kbase, ks_s);              // K(i+1) streams in during the PV phase
 #pragma unroll
             for (int g = 0; g < G; ++g) s[g] = valid ? s[g] * a.scale_log2 : -INFINITY;
 
-            // online softmax with a lazy max: rescale only when a score exceeds the running max by 2^kRescaleMargin
-            float alpha[4] = {1.f, 1.f, 1.f, 1.f};
+            // ------------------------------------------------ online softmax (lazy max: rescale only when needed)
             bool need = false;
 #pragma unroll
-            for (int g = 0; g < G; ++g) need = need || (s[g] > run_m[g] + kRescaleMargin);
+            for (int g = 0; g < G; ++g) need = need || (s[g] > st.m[g] + kRescaleMargin);
             if (__any_sync(0xffffffffu, need)) {
+                // flush the packed-half PV accumulators first: they are relative to the old max
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float2 f = __half22float2(acc[sl][g]);
+                        st.o[sl][g][0] += f.x; st.o[sl][g][1] += f.y;
+                        acc[sl][g] = __float2half2_rn(0.f);
+                    }
+                since_flush = 0;
+                float nm[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) nm[g] = fmaxf(st.m[g], warp_max(s[g]));
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const float nm = fmaxf(run_m[g], warp_max(s[g]));
-                    if (nm > run_m[g]) {
-                        alpha[g] = exp2_safe(run_m[g], nm);
-                        run_l[g] *= alpha[g];
-                        run_m[g] = nm;
+                    if (nm[g] > st.m[g]) {
+                        const float alpha = exp2_safe(st.m[g], nm[g]);
+                        st.l[g] *= alpha;
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl) { st.o[sl][g][0] *= alpha; st.o[sl][g][1] *= alpha; }
+                        st.m[g] = nm[g];
                     }
                 }
             }
             float p[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                p[g] = exp2_safe(s[g], run_m[g]);
-                run_l[g] += p[g];
+                p[g] = exp2_safe(s[g], st.m[g]);
+                st.l[g] += p[g];
             }
-            if (n > 0) mbar_wait(bar_empty, (n - 1) & 1);   // the PV warp has consumed the previous tile's slot
-            *reinterpret_cast<uint2*>(pslot + lane * 8) = make_uint2(as_u32(__floats2half2_rn(p[0], p[1])), as_u32(__floats2half2_rn(p[2], p[3])));
-            if (lane == 0) *reinterpret_cast<float4*>(pslot + kTile * 8) = make_float4(alpha[0], alpha[1], alpha[2], alpha[3]);
+            // p for the PV phase: 4 halves (8 bytes) per token
+            *reinterpret_cast<uint2*>(pbuf_w + lane * 8) = make_uint2(as_u32(__floats2half2_rn(p[0], p[1])), as_u32(__floats2half2_rn(p[2], p[3])));
+
+            cp_async_wait<1>();          // pending [V(i), K(i+1)] -> V(i) landed
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full);
-        }
-        cp_async_wait<0>();
-    } else if (has_codes) {
-        // ================================================================ PV warp
-        unsigned char* vsp = stage_p + (kPairs + pair) * kTileBytes;
-        const uint32_t vs_s = smem_u32(vsp);
-        const uint8_t* vbase = a.v_codes + (a.v_layout == MILLION_V_PAGED ? 0 : hb * a.v_head_stride);
-        // slot s -> byte bb = (s + hw) & 3 of the lane's V code word; column offset col_of(4*lq + bb) * 4
-        uint32_t voff01, voff23, vsel[4];
-        {
-            uint32_t o[4];
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl) {
-                const int bb = (sl + hw) & 3;
-                o[sl] = (uint32_t)(col_of(4 * lq + bb) * 4);
-                vsel[sl] = (uint32_t)(4 + (sl & 1)) | ((uint32_t)bb << 4) | (6u << 8) | (6u << 12);   // [off, code byte bb, 0, 0]
-            }
-            voff01 = o[0] | (o[1] << 8);
-            voff23 = o[2] | (o[3] << 8);
-        }
-        auto issue_v = [&](int tile) {
-            const int tok0 = t0 + tile * kTile;
-            const bool in_range = tile < n_tiles;
-            if constexpr (VL == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int chunk = lane + i * 32;
-                    const int tok = tok0 + (chunk >> 2);
-                    const int ok = (in_range && tok < t1) ? 16 : 0;
-                    cp_async16(vs_s + chunk * 16, vbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
-                }
-            } else {
-                // transposed value codes: the tile is 64 sub-space rows of 32 tokens; row m is staged at row pi(m) = m/4 + 16*(m%4)
-                // (32 bytes each) so that the word reads of the PV phase below are bank-conflict free
-                const uint8_t* src0 = vbase;
-                int64_t row_stride = a.v_ld;
-                if (in_range) {
-                    if (a.v_layout == MILLION_V_PAGED) {
-                        const int64_t page = __ldg(a.v_page_ids + (int64_t)hb * a.n_pages + tok0 / a.page_size);
-                        src0 = a.v_codes + page * 64 * a.page_size + (tok0 % a.page_size);
-                        row_stride = a.page_size;
-                    } else {
-                        src0 = vbase + tok0;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int chunk = lane + i * 32;            // 0..127: 64 rows * 2 chunks of 16 tokens
-                    const int m = chunk >> 1, hc = chunk & 1;
-                    int ok = in_range ? (t1 - (tok0 + hc * 16)) : 0;
-                    ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
-                    const uint32_t dst = vs_s + (uint32_t)((((m >> 2) + 16 * (m & 3)) * 32) + hc * 16);
-                    cp_async16(dst, (ok ? src0 : vbase) + (ok ? (int64_t)m * row_stride + hc * 16 : 0), ok);
-                }
-            }
-            cp_async_commit();
-        };
-        issue_v(pair);
-        __half2 acc[4][G];
-#pragma unroll
-        for (int sl = 0; sl < 4; ++sl)
-#pragma unroll
-            for (int g = 0; g < G; ++g) acc[sl][g] = __float2half2_rn(0.f);
-        auto flush = [&]() {
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl)
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float2 f = __half22float2(acc[sl][g]);
-                    out_o[sl][g][0] += f.x; out_o[sl][g][1] += f.y;
-                    acc[sl][g] = __float2half2_rn(0.f);
-                }
-        };
-        int since_flush = 0, n = 0;
-        for (int tile = pair; tile < n_tiles; tile += kPairs, ++n) {
-            cp_async_wait<0>();                             // V(n) landed
-            mbar_wait(bar_full, n & 1);                     // p(n) and the rescale factors are in the slot
-            __syncwarp();
-            {
-                const float4 al = *reinterpret_cast<const float4*>(pslot + kTile * 8);
-                const float alv[4] = {al.x, al.y, al.z, al.w};
-                bool resc = false;
-#pragma unroll
-                for (int g = 0; g < G; ++g) resc = resc || (alv[g] != 1.f);
-                if (resc) {                                 // warp-uniform: the running max moved
-                    flush();
-                    since_flush = 0;
-#pragma unroll
-                    for (int g = 0; g < G; ++g)
-#pragma unroll
-                        for (int sl = 0; sl < 4; ++sl) { out_o[sl][g][0] *= alv[g]; out_o[sl][g][1] *= alv[g]; }
-                }
-            }
+
+            // ------------------------------------------------ PV: lane owns 4 sub-spaces (slot k -> 4*lq + ((k + hw) & 3))
             if constexpr (VL == 0) {
                 // row-major codes: a half-warp per token, the lane's word holds its 4 sub-spaces of that token
 #pragma unroll 4
                 for (int jp = 0; jp < kTile / 2; ++jp) {
                     const int j = 2 * jp + hw;
                     const uint32_t word = lds32(vsp, j * kRowBytes + lq * 4);
-                    const uint2 pk = lds64(pslot, j * 8);
+                    const uint2 pk = lds64(pbuf_w, j * 8);
                     const __half2 p01 = as_h2(pk.x), p23 = as_h2(pk.y);
 #pragma unroll
                     for (int sl = 0; sl < 4; ++sl) {
@@ -459,7 +427,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
                     uint32_t wv[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) wv[k] = lds32(vsp, (lq + 16 * ((k + hw) & 3)) * 32 + hw * 16 + tgl * 4);
-                    const uint4 pa = lds128(pslot, tg * 32), pb = lds128(pslot, tg * 32 + 16);
+                    const uint4 pa = lds128(pbuf_w, tg * 32), pb = lds128(pbuf_w, tg * 32 + 16);
                     const uint32_t pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -479,24 +447,39 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
                     }
                 }
             }
-            __syncwarp();                                   // every lane is done with the V tile and the p slot
-            if (lane == 0) mbar_arrive(bar_empty);
-            issue_v(tile + kPairs);                         // V(n+1) streams in while the QK warp scores the next tile
-            if (++since_flush == 2) { flush(); since_flush = 0; }   // packed-half partial sums live for at most 2 tiles
+            __syncwarp();                                   // every lane is done with the V tile and the p slots
+            issue_v(tile + kWarps);                          // V(i+1) streams in during the next QK phase
+            if (++since_flush == 2) {                       // packed-half partial sums live for at most 2 tiles (32 terms)
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float2 f = __half22float2(acc[sl][g]);
+                        st.o[sl][g][0] += f.x; st.o[sl][g][1] += f.y;
+                        acc[sl][g] = __float2half2_rn(0.f);
+                    }
+                since_flush = 0;
+            }
         }
-        flush();
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float2 f = __half22float2(acc[sl][g]);
+                st.o[sl][g][0] += f.x; st.o[sl][g][1] += f.y;
+            }
         cp_async_wait<0>();
     }
 
     // ---------------------------------------------------------------- my share of the fp16 window (exact attention)
-    // The r recent tokens are dealt out to the splits of the group (r/S tokens each); inside the CTA the QK warps take one
-    // token at a time.  Lane owns dims 4*lane .. 4*lane+3.
+    // The r recent tokens are dealt out to the splits of the group (r/S tokens each, one token per warp at a time), so no
+    // CTA carries a long serial tail.  Lane owns dims 4*lane .. 4*lane+3.
     float wm[G], wl[G], wo[G][4];
 #pragma unroll
     for (int g = 0; g < G; ++g) { wm[g] = -INFINITY; wl[g] = 0.f; wo[g][0] = wo[g][1] = wo[g][2] = wo[g][3] = 0.f; }
-    if (is_qk) {
+    {
         const int w0 = (int)((long long)a.r * split / a.n_splits), w1 = (int)((long long)a.r * (split + 1) / a.n_splits);
-        if (w0 + pair < w1) {
+        if (w0 + warp < w1) {
             float qv[G][4];
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -504,7 +487,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
                 const float2 q01 = io<T>::to_f2(qr.x), q23 = io<T>::to_f2(qr.y);
                 qv[g][0] = q01.x * a.scale_log2; qv[g][1] = q01.y * a.scale_log2; qv[g][2] = q23.x * a.scale_log2; qv[g][3] = q23.y * a.scale_log2;
             }
-            for (int t = w0 + pair; t < w1; t += kPairs) {
+            for (int t = w0 + warp; t < w1; t += kWarps) {
                 const int64_t row = ((int64_t)hb * a.res_len + t) * 128 + 4 * lane;
                 const uint2 kr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
                 const uint2 vr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
@@ -527,58 +510,60 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     __syncthreads();   // every warp is done with its stage buffers and p slots (aliased below)
     dbg_stamp(a, 2);
     // ---------------------------------------------------------------- combine the warps of this CTA -> one partial state
-    // 2 * kPairs entries of [G*128 o | G m | G l]: entry p = coded tokens of pair p (o from its PV warp, m and l from its QK
-    // warp), entry kPairs + p = the window tokens of QK warp p.
+    // 2 * kWarps entries of [G*128 o | G m | G l]: entry w = coded tokens of warp w, entry kWarps + w = its window tokens.
     // Coded layout: slot sl of lane (hw, lq) holds sub-space 4*lq + ((sl + hw) & 3); hw=1 is folded into hw=0 first.
     constexpr int kEntry = (G * 130 + 3) & ~3;   // 16-byte aligned entries
     {
-        float* wx = xch + pair * kEntry;
-        if (!is_qk) {
+        const int lq = lane & 15, hw = lane >> 4;
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl)
+        for (int g = 0; g < G; ++g) st.l[g] = warp_sum(st.l[g]);
+        float* wx = xch + warp * kEntry;
 #pragma unroll
-                for (int g = 0; g < G; ++g)
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        // partner (hw=1) slot (sl - 1) & 3 holds the same sub-space as my (hw=0) slot sl
-                        const float theirs = __shfl_xor_sync(0xffffffffu, out_o[(sl + 3) & 3][g][k], 16);
-                        if (hw == 0) wx[g * 128 + 2 * (4 * lq + sl) + k] = out_o[sl][g][k] + theirs;
-                    }
-        } else {
-#pragma unroll
-            for (int g = 0; g < G; ++g) run_l[g] = warp_sum(run_l[g]);
-            float* ww = xch + (kPairs + pair) * kEntry;
+        for (int sl = 0; sl < 4; ++sl)
 #pragma unroll
             for (int g = 0; g < G; ++g)
-                *reinterpret_cast<float4*>(ww + g * 128 + 4 * lane) = make_float4(wo[g][0], wo[g][1], wo[g][2], wo[g][3]);
-            if (lane == 0) {
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    wx[G * 128 + g] = run_m[g]; wx[G * 128 + G + g] = run_l[g];
-                    ww[G * 128 + g] = wm[g];    ww[G * 128 + G + g] = wl[g];
+                for (int k = 0; k < 2; ++k) {
+                    // partner (hw=1) slot (sl - 1) & 3 holds the same sub-space as my (hw=0) slot sl
+                    const float theirs = __shfl_xor_sync(0xffffffffu, st.o[(sl + 3) & 3][g][k], 16);
+                    if (hw == 0) wx[g * 128 + 2 * (4 * lq + sl) + k] = st.o[sl][g][k] + theirs;
                 }
+        float* ww = xch + (kWarps + warp) * kEntry;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            *reinterpret_cast<float4*>(ww + g * 128 + 4 * lane) = make_float4(wo[g][0], wo[g][1], wo[g][2], wo[g][3]);
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                wx[G * 128 + g] = st.m[g]; wx[G * 128 + G + g] = st.l[g];
+                ww[G * 128 + g] = wm[g];   ww[G * 128 + G + g] = wl[g];
             }
         }
     }
     __syncthreads();
     {
-        // thread -> (dim = tid & 127, head = tid >> 7)
-        const int dim = tid & 127, g = tid >> 7;
-        if (g < G) {
-            float mstar = -INFINITY;
+        // thread -> (dim = tid & 127, head half = tid >> 7)
+        constexpr int GH = G >= 2 ? G / 2 : 1;
+        const int dim = tid & 127, hsel = tid >> 7;
+        if (G >= 2 || hsel == 0) {
 #pragma unroll
-            for (int e = 0; e < 2 * kPairs; ++e) mstar = fmaxf(mstar, xch[e * kEntry + G * 128 + g]);
-            float o = 0.f, l = 0.f;
+            for (int gi = 0; gi < GH; ++gi) {
+                const int g = (G >= 2 ? hsel * GH : 0) + gi;
+                float mstar = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 2 * kPairs; ++e) {
-                const float* ex = xch + e * kEntry;
-                const float sc = exp2_safe(ex[G * 128 + g], mstar);
-                o = fmaf(ex[g * 128 + dim], sc, o);
-                l = fmaf(ex[G * 128 + G + g], sc, l);
+                for (int e = 0; e < 2 * kWarps; ++e) mstar = fmaxf(mstar, xch[e * kEntry + G * 128 + g]);
+                float o = 0.f, l = 0.f;
+#pragma unroll
+                for (int e = 0; e < 2 * kWarps; ++e) {
+                    const float* ex = xch + e * kEntry;
+                    const float sc = exp2_safe(ex[G * 128 + g], mstar);
+                    o = fmaf(ex[g * 128 + dim], sc, o);
+                    l = fmaf(ex[G * 128 + G + g], sc, l);
+                }
+                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * a.n_parts + split) * 130;
+                part[dim] = o;
+                if (dim == 0) { part[128] = mstar; part[129] = l; }
             }
-            float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * a.n_parts + split) * 130;
-            part[dim] = o;
-            if (dim == 0) { part[128] = mstar; part[129] = l; }
         }
     }
     dbg_stamp(a, 3);
@@ -594,10 +579,10 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
 template <typename T, int G, int VL>
 static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
-    const size_t smem = LutCfg<G>::bytes + kVtabBytes + 2 * kPairs * kTileBytes + kPairs * kPSlot + kPairs * 16 + 64;
-    static_assert(2 * kPairs * kTileBytes + kPairs * kPSlot >= 2 * kPairs * 4 * 130 * sizeof(float), "stage + p area too small for the combine");
-    static_assert(2 * kPairs * kTileBytes >= 2 * 16384, "stage area too small for the LUT-build chunks");
-    static_assert(2 * kPairs * kTileBytes + kPairs * kPSlot >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
+    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + 256;
+    static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= 2 * kWarps * 4 * 130 * sizeof(float), "stage + p area too small for the combine");
+    static_assert(kWarps * kStageBytes >= 2 * 16384, "stage area too small for the LUT-build chunks");
+    static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static bool configured = false;
     if (!configured) {
         MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
