@@ -23,7 +23,10 @@ struct AttnArgs {
     int bs, nh, nh_k, d, M, C, nk, r, res_len;
     int v_layout, page_size, n_pages;
     int n_splits;         // CTAs over the coded tokens
-    int n_parts;          // partial states per head: generic n_splits + 1 (window = extra part), fast n_splits
+    int n_parts;          // part SLOTS per head in `parts` (stride); how many are valid is decided per group
+    int ws_parts;         // part slots per head that fit in the caller's workspace
+    int auto_splits;      // the caller left the split count to us (flat scheduling allowed)
+    int flat, flat_per, flat_ug;   // flat scheduling: CTA c owns 64-token units [c*flat_per, (c+1)*flat_per) of the (group, unit) space
     int units_per_split;  // 16-token units per split
     float scale_log2;     // log2(e)/sqrt(d)
     unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 8 globaltimer stamps per CTA
@@ -54,7 +57,7 @@ __device__ __forceinline__ int v_code_at(const AttnArgs& a, int hb, int j, int m
     return a.v_codes[(page * a.M + m) * a.page_size + (j % a.page_size)];
 }
 
-// Merge the a.n_parts partial states of every query head of group (b, hk) and write the result.
+// Merge the first n_parts partial states of every query head of group (b, hk) and write the result.
 // Called by the last CTA of the group (after the ticket), all threads of the block participate.
 // Algebra of flash_decoding_reduce_kernel (Kernel.cuh:1249-1269) on un-normalised fp32 partials.
 // All heads are merged together in two rounds of independent loads (one for (m, l), one for o): a serial chain of L2
@@ -62,9 +65,9 @@ __device__ __forceinline__ int v_code_at(const AttnArgs& a, int hb, int j, int m
 // `scr` = shared scratch of kMergeScratch floats.
 constexpr int kMergeScratch = 3 * 2048 + 64;
 template <typename T>
-__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, float* scr) {
+__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, int n_parts, float* scr) {
     const int G = a.nh / a.nh_k;
-    const int n_parts = a.n_parts;
+    const int slots = a.n_parts;
     const int stride = a.d + 2;
     float* mm = scr;               // [gc][n_parts] running max of each part
     float* ll = scr + 2048;        // [gc][n_parts] denominators
@@ -75,10 +78,11 @@ __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, fl
     for (int g0 = 0; g0 < G; g0 += gc_max) {
         const int gc = min(gc_max, G - g0);
         const int h0 = hk * G + g0;
-        const float* base = a.parts + ((int64_t)(b * a.nh + h0) * n_parts) * stride;   // heads are contiguous
+        const float* base = a.parts + ((int64_t)(b * a.nh + h0) * slots) * stride;   // head g, part i at (g*slots + i)*stride
         for (int idx = threadIdx.x; idx < gc * n_parts; idx += blockDim.x) {
-            mm[idx] = __ldcg(base + (int64_t)idx * stride + a.d);
-            ll[idx] = __ldcg(base + (int64_t)idx * stride + a.d + 1);
+            const int64_t off = (int64_t)((idx / n_parts) * slots + idx % n_parts) * stride;
+            mm[idx] = __ldcg(base + off + a.d);
+            ll[idx] = __ldcg(base + off + a.d + 1);
         }
         __syncthreads();
         if (threadIdx.x < gc) {
@@ -99,7 +103,7 @@ __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, fl
         __syncthreads();
         for (int idx = threadIdx.x; idx < gc * a.d; idx += blockDim.x) {
             const int g = idx / a.d, k = idx % a.d;
-            const float* src = base + (int64_t)g * n_parts * stride + k;
+            const float* src = base + (int64_t)g * slots * stride + k;
             const float* w = ww + g * n_parts;
             float acc = 0.f;
             int i = 0;

@@ -29,6 +29,7 @@ constexpr int kTile = 32;                       // tokens per warp tile
 constexpr int kRowBytes = 64;                   // M = 64 one-byte codes
 constexpr int kStageBytes = 2 * kTile * kRowBytes;   // one K tile + one V tile per warp
 constexpr int kVtabBytes = 64 * 1024;
+constexpr int kFlatPad = 24;                    // cost of one more (prologue + epilogue) in 64-token units (~9 us)
 constexpr float kRescaleMargin = 6.f;           // log2 units: p <= 64 before a rescale is forced
 
 template <int G> struct LutCfg;
@@ -130,9 +131,11 @@ __device__ __forceinline__ uint32_t gather32(uint32_t r) {
 
 }  // namespace fast
 
-// VL = 0: value codes row-major (tokens x 64 bytes); VL = 1: transposed per sub-space (paged pool or (M, ld) rows)
+// One segment = the coded tokens [t0, t1) of group (b, hk) (+ this CTA's share of the window), written as part `split` of
+// `np` parts of that group.
 template <typename T, int G, int VL>
-__global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
+__device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint32_t* __restrict__ prepared, const int gsub, const int split,
+                                                  const int hk, const int sub, const int b, const int t0, const int t1, const int np) {
     using namespace fast;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr uint32_t kLutOff = 0, kVtabOff = LutCfg<G>::bytes, kStageOff = kVtabOff + kVtabBytes;
@@ -152,14 +155,9 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         __trap();
     }
     dbg_stamp(a, 0);
-    const int split = blockIdx.x;
-    // blockIdx.y enumerates (kv head, 4-head sub-group) when the GQA group is larger than 4
-    const int hk = blockIdx.y / gsub, sub = blockIdx.y % gsub, b = blockIdx.z;
     const int Gfull = a.nh / a.nh_k;
     const int h0 = hk * Gfull + sub * G;                                // first query head of this CTA
     const int hb = b * a.nh_k + hk;
-    int t0, t1;
-    split_range(a, split, t0, t1);
     const bool has_codes = t1 > t0;
 
     // ---------------------------------------------------------------- prologue: V table + K LUT
@@ -478,7 +476,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
 #pragma unroll
     for (int g = 0; g < G; ++g) { wm[g] = -INFINITY; wl[g] = 0.f; wo[g][0] = wo[g][1] = wo[g][2] = wo[g][3] = 0.f; }
     {
-        const int w0 = (int)((long long)a.r * split / a.n_splits), w1 = (int)((long long)a.r * (split + 1) / a.n_splits);
+        const int w0 = (int)((long long)a.r * split / np), w1 = (int)((long long)a.r * (split + 1) / np);
         if (w0 + warp < w1) {
             float qv[G][4];
 #pragma unroll
@@ -569,10 +567,42 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     dbg_stamp(a, 3);
     dbg_stamp(a, 4);
     // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
-    const bool last = last_cta_of_group(a.counters, hb, a.n_splits * gsub, flag);
+    const bool last = last_cta_of_group(a.counters, hb, np * gsub, flag);
     dbg_stamp(a, 5);
-    if (last) merge_group<T>(a, b, hk, xch);
+    if (last) merge_group<T>(a, b, hk, np, xch);
     dbg_stamp(a, 6);
+}
+
+// VL = 0: value codes row-major (tokens x 64 bytes); VL = 1: transposed per sub-space (paged pool or (M, ld) rows)
+template <typename T, int G, int VL>
+__global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
+    if (!a.flat) {
+        // grid (splits, kv heads x 4-head sub-groups, batch): one segment per CTA
+        int t0, t1;
+        split_range(a, blockIdx.x, t0, t1);
+        attn_fast_segment<T, G, VL>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits);
+        return;
+    }
+    // Flat scheduling: the (group, 64-token unit) space is cut into runs of equal COST, one per CTA, so every SM gets the
+    // same amount of work whatever bs*nh_k is (64 groups on 148 SMs would otherwise use 128).  A run may cross a group
+    // boundary: the CTA then works the two pieces one after the other (LUT rebuilt), which costs a second prologue and
+    // epilogue — every group is therefore preceded by kFlatPad virtual units in the space that is cut, so a CTA that
+    // starts a new group inside its run gets that many fewer real units.  Part index inside a group = CTA index minus
+    // the group's first CTA; everything is recomputed from (flat_per, flat_ug).
+    const int ug = a.flat_ug, per = a.flat_per, vg = ug + fast::kFlatPad;
+    const long long total = (long long)a.bs * a.nh_k * vg;
+    const long long run0 = (long long)blockIdx.x * per;
+    const long long run1 = (run0 + per < total) ? run0 + per : total;
+    for (int grp = (int)(run0 / vg); grp < a.bs * a.nh_k && (long long)grp * vg < run1; ++grp) {
+        const long long real0 = (long long)grp * vg + fast::kFlatPad, real1 = real0 + ug;   // this group's real units in the cut space
+        const long long s0 = run0 > real0 ? run0 : real0, s1 = run1 < real1 ? run1 : real1;
+        if (s1 <= s0) continue;
+        const int first = (int)(real0 / per), last = (int)((real1 - 1) / per);
+        const int us = (int)(s0 - real0), ue = (int)(s1 - real0);
+        const int t1 = (ue * 64 < a.nk) ? ue * 64 : a.nk;
+        attn_fast_segment<T, G, VL>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1);
+        __syncthreads();   // the next piece reuses every shared buffer
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
@@ -589,6 +619,7 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
         configured = true;
     }
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
+    if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
     attn_fast_kernel<T, G, VL><<<grid, block, smem, stream>>>(a, prepared, gsub);
     MILLION_CUDA_OK(cudaGetLastError());
     return MILLION_OK;
@@ -597,6 +628,7 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
 int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only) {
     AttnArgs a = a_in;
     a.n_parts = a.n_splits;   // the window is dealt out to the splits, no extra part
+    a.flat = 0;
     const int Gfull = a.nh / a.nh_k;
     if (a.d != 128 || a.M != 64 || a.C != 256) MILLION_UNSUPPORTED("fast decode attention needs d=128, M=64, C=256");
     if (!(Gfull == 1 || Gfull == 2 || Gfull % 4 == 0)) MILLION_UNSUPPORTED("fast decode attention needs nh/nh_k in {1,2,4k}");
@@ -612,6 +644,24 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     if (a.r > 0 && (((uintptr_t)a.k_res | (uintptr_t)a.v_res) & 7)) MILLION_UNSUPPORTED("fast decode attention needs an 8-byte aligned window");
     if (probe_only) return MILLION_OK;
     const int G = Gfull >= 4 ? 4 : Gfull, gsub = Gfull >= 4 ? Gfull / 4 : 1;
+    if (a.auto_splits && gsub == 1 && a.nk > 0) {
+        // flat scheduling pays when a CTA's share of tokens dwarfs the (up to two) prologues it runs
+        int sms = sm_count();
+        if (sms <= 0) sms = 148;
+        const long long groups = (long long)a.bs * a.nh_k;
+        const int ug = (a.nk + 63) / 64;
+        const long long total = groups * (ug + fast::kFlatPad);            // cost space: see attn_fast_kernel
+        const long long ncta = groups * ug < sms ? groups * ug : sms;
+        const int per = (int)((total + ncta - 1) / ncta);
+        const int max_parts = (ug + per - 1) / per + 1;
+        const double P = fast::kFlatPad * 64.0;   // prologue + epilogue of one piece, in tokens
+        const long long ctas = groups * a.n_splits;
+        const double split_cost = (double)((ctas + sms - 1) / sms) * ((double)a.units_per_split * 16 + P);
+        const double flat_cost = (double)per * 64 + P;   // every CTA runs at least one prologue/epilogue
+        if (flat_cost < 0.93 * split_cost && max_parts <= a.ws_parts && max_parts <= 1024) {
+            a.flat = 1; a.flat_per = per; a.flat_ug = ug; a.n_parts = max_parts;
+        }
+    }
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
 #define MILLION_FAST_CASE(TT, GG) \
     return a.v_layout == MILLION_V_ROWMAJOR ? launch_fast_t<TT, GG, 0>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1>(a, prep, gsub, stream)

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
             if (tid + u * 128 < a.d) part[tid + u * 128] = acc[u];
         if (tid == 0) { part[a.d] = run_m; part[a.d + 1] = run_l; }
     }
-    if (last_cta_of_group(a.counters, hb, n_parts, &flag)) merge_group<T>(a, b, hk, mscr);
+    if (last_cta_of_group(a.counters, hb, n_parts, &flag)) merge_group<T>(a, b, hk, n_parts, mscr);
 }
 
 int launch_attn_generic(const AttnArgs& a_in, int io_dtype, cudaStream_t stream) {

@@ -230,7 +230,7 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
         p.k_res, p.v_res = k_res.data_ptr(), v_res.data_ptr()
     splits = n_splits or default_splits(bs, nh_k, nk)
     ws = workspace if workspace is not None else attn_workspace(q.device, bs, nh, nh_k, d, splits)
-    p.workspace, p.workspace_bytes, p.n_splits = ws.data_ptr(), ws.numel(), splits
+    p.workspace, p.workspace_bytes, p.n_splits = ws.data_ptr(), ws.numel(), n_splits   # 0 = library's choice (may schedule flat)
     if partial is not None:
         assert partial.dtype == torch.float32 and partial.is_contiguous() and partial.numel() == bs * nh * (d + 2)
         p.partial = partial.data_ptr()
