@@ -107,18 +107,29 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
 }
 
 // row minimum of 64 values and, relative to thr = min(best_so_far, that minimum) + eps, the candidate bits
-// (bit 31 of word 0 = first column).  Returns the chunk minimum.
+// (bit 31 of word 0 = first column).  Returns the chunk minimum.  Four independent min chains and eight independent
+// bit-collection chains (8 columns each): a single 32-long dependent chain per word made the epilogue latency bound.
 __device__ __forceinline__ float reduce_chunk(const float (&v)[64], float best_so_far, float eps, uint32_t& w0, uint32_t& w1) {
-    float m = v[0];
+    float m0 = v[0], m1 = v[16], m2 = v[32], m3 = v[48];
 #pragma unroll
-    for (int i = 1; i + 1 < 64; i += 2) m = min3(m, v[i], v[i + 1]);
-    m = fminf(m, v[63]);
+    for (int i = 1; i + 1 < 16; i += 2) {
+        m0 = min3(m0, v[i], v[i + 1]);
+        m1 = min3(m1, v[16 + i], v[17 + i]);
+        m2 = min3(m2, v[32 + i], v[33 + i]);
+        m3 = min3(m3, v[48 + i], v[49 + i]);
+    }
+    const float m = fminf(min3(m0, v[15], m1), min3(min3(m2, v[31], v[47]), m3, v[63]));
     const float thr = fminf(best_so_far, m) + eps;
-    w0 = 0; w1 = 0;
+    uint32_t q[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) w0 = __funnelshift_l(__float_as_uint(v[i] - thr), w0, 1);        // sign(v - thr) = 1 <=> v < thr
+    for (int c = 0; c < 8; ++c) q[c] = 0;
 #pragma unroll
-    for (int i = 32; i < 64; ++i) w1 = __funnelshift_l(__float_as_uint(v[i] - thr), w1, 1);
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = __funnelshift_l(__float_as_uint(v[8 * c + i] - thr), q[c], 1);   // sign(v - thr) = 1 <=> v < thr
+    }
+    w0 = (q[0] << 24) | (q[1] << 16) | (q[2] << 8) | q[3];
+    w1 = (q[4] << 24) | (q[5] << 16) | (q[6] << 8) | q[7];
     return m;
 }
 
@@ -148,31 +159,33 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Two warpgroups (4 warps = 128 threads = the 128 token rows of a tile) work on alternating items, each with its own
-// A slot, TMEM buffer (256 columns) and mbarrier: while one group waits for its MMA the other one is in its epilogue.
+// Two warpgroups (4 warps = 128 threads = the 128 token rows of a tile); warpgroup g takes the sub-spaces j = g, g+2, ...
+// of every tile.  An item (tile, j) is issued as TWO N=128 MMAs into the two 128-column halves of the group's TMEM
+// region, each with its own mbarrier: while the CUDA cores reduce one half, the tensor core already works on the other
+// half or on the next item, so the MMA latency is off the critical path.
 template <typename T, int DM>
 __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* Bs = smem;                                   // kMG * 4 KB
-    unsigned char* As = Bs + kMG * kBTileBytes;                 // 2 slots * 2 KB (one per warpgroup)
-    unsigned char* Zs = As + 2 * kATileBytes;                   // 4 KB of zeros (second K chunk of both operands)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Zs + kZeroBytes);   // 2 mbarriers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    unsigned char* As = Bs + kMG * kBTileBytes;                 // 2 warpgroups * 2 slots * 2 KB
+    unsigned char* Zs = As + 4 * kATileBytes;                   // 4 KB of zeros (second K chunk of both operands)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Zs + kZeroBytes);   // 2 warpgroups * 2 halves
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     float* cmax_s = reinterpret_cast<float*>(tmem_slot + 2);    // kMG floats
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int wg = warp >> 2, row = tid & 127;                  // warpgroup, token row inside the tile
     const int m0 = blockIdx.y * kMG;
     constexpr uint32_t kOne = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
     constexpr uint32_t kFmt = std::is_same<T, __half>::value ? 0u : 1u;
-    // instruction descriptor: D fp32, A/B format, both K-major, N = 256, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: D fp32, A/B format, both K-major, N = 128, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
     // ---- one-time setup
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     if (tid == 32) {
-        mbar_init(smem_u32(&bars[0]), 1);
-        mbar_init(smem_u32(&bars[1]), 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -189,68 +202,107 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t zs = smem_u32(Zs);
-    const uint32_t as = smem_u32(As + wg * kATileBytes);
-    const uint32_t bar = smem_u32(&bars[wg]);
+    const uint32_t bar0 = smem_u32(&bars[wg * 2]), bar1 = bar0 + 8;
     const uint32_t dcol = tmem_base + wg * 256;
     const uint32_t taddr = dcol + ((uint32_t)((warp & 3) * 32) << 16);   // my TMEM lane quarter
+    unsigned char* Aw = As + wg * 2 * kATileBytes;
 
-    // items of this CTA: (tile, j) for tile = blockIdx.x, += gridDim.x and j < kMG; warpgroup wg takes every other one
     const int n_my_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_items = n_my_tiles * kMG;
-    uint32_t phase = 0;
-    for (int item = wg; item < n_items; item += 2) {
-        const int tile = blockIdx.x + (item / kMG) * gridDim.x, j = item % kMG;
-        const int head = tile / a.tiles_per_head;
-        const int tok = (tile % a.tiles_per_head) * kTokTile + row;
-        const bool live = tok < a.n_tokens;
+    const int n_items = n_my_tiles * (kMG / 2);
 
-        // ---- A row of my token for sub-space m0 + j, |x_m|^2
-        uint32_t xw[DM / 2];
-        {
-            const uint32_t* xp = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(a.x) + head * a.x_head_stride +
-                                                                   (int64_t)(live ? tok : 0) * a.d + (m0 + j) * DM);
+    // state of the item being built / issued next
+    int nx_tile = blockIdx.x, nx_jj = 0, nx_head = 0, nx_tok = 0;
+    bool nx_live = false;
+    uint32_t nx_xw[DM / 2];
+    auto locate = [&]() {     // (head, token) of my row in tile nx_tile — once per tile, the only integer divisions
+        nx_head = nx_tile / a.tiles_per_head;
+        nx_tok = (nx_tile - nx_head * a.tiles_per_head) * kTokTile + row;
+        nx_live = nx_tile < a.total_tiles && nx_tok < a.n_tokens;
+    };
+    auto fetch_x = [&]() {    // my token's values for sub-space m0 + wg + 2*nx_jj
+        const uint32_t* xp = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(a.x) + nx_head * a.x_head_stride +
+                                                               (int64_t)(nx_live ? nx_tok : 0) * a.d + (m0 + wg + 2 * nx_jj) * DM);
 #pragma unroll
-            for (int i = 0; i < DM / 2; ++i) xw[i] = live ? __ldg(xp + i) : 0u;
-        }
+        for (int i = 0; i < DM / 2; ++i) nx_xw[i] = nx_live ? __ldg(xp + i) : 0u;
+    };
+    auto build_and_issue_half0 = [&](int slot) {   // A row -> smem slot, group barrier, MMA half 0
         uint4 rowv;
-        if constexpr (DM == 2) rowv = make_uint4(xw[0], kOne | (kOne << 16), kOne, 0u);
-        else rowv = make_uint4(xw[0], xw[1], kOne | (kOne << 16), kOne);
-        *reinterpret_cast<uint4*>(As + wg * kATileBytes + row * 16) = rowv;
+        if constexpr (DM == 2) rowv = make_uint4(nx_xw[0], kOne | (kOne << 16), kOne, 0u);
+        else rowv = make_uint4(nx_xw[0], nx_xw[1], kOne | (kOne << 16), kOne);
+        *reinterpret_cast<uint4*>(Aw + slot * kATileBytes + row * 16) = rowv;
         fence_async_proxy();
-        tc_fence_before();                       // my tcgen05.ld of the previous item are done (wait::ld) and ordered
+        tc_fence_before();
         named_bar_sync(1 + wg, 128);
         tc_fence_after();
         if (row == 0) {
-            const uint32_t bs = smem_u32(Bs + j * kBTileBytes);
+            const uint32_t as = smem_u32(Aw + slot * kATileBytes), bs = smem_u32(Bs + (wg + 2 * nx_jj) * kBTileBytes);
             umma_f16(dcol, make_desc(as, zs - as, 128), make_desc(bs, zs - bs, 128), idesc);
-            umma_commit(bar);
+            umma_commit(bar0);
         }
+    };
+    auto issue_half1 = [&](int slot) {
+        tc_fence_before();
+        named_bar_sync(1 + wg, 128);
+        tc_fence_after();
+        if (row == 0) {
+            const uint32_t as = smem_u32(Aw + slot * kATileBytes), bs = smem_u32(Bs + (wg + 2 * nx_jj) * kBTileBytes + 128 * 16);
+            umma_f16(dcol + 128, make_desc(as, zs - as, 128), make_desc(bs, zs - bs, 128), idesc);
+            umma_commit(bar1);
+        }
+    };
+    auto advance = [&]() {
+        if (++nx_jj == kMG / 2) { nx_jj = 0; nx_tile += gridDim.x; locate(); }
+    };
+
+    if (n_items > 0) {
+        locate();
+        fetch_x();
+        build_and_issue_half0(0);
+        issue_half1(0);
+    }
+    for (int i = 0; i < n_items; ++i) {
+        // ---- the item whose MMAs are in flight becomes the current one
+        const int head = nx_head, tok = nx_tok, j = wg + 2 * nx_jj;
+        const bool live = nx_live;
         float xv[DM];
         {
-            const float2 f0 = io<T>::to_f2(xw[0]);
+            const float2 f0 = io<T>::to_f2(nx_xw[0]);
             xv[0] = f0.x; xv[1] = f0.y;
-            if constexpr (DM == 4) { const float2 f1 = io<T>::to_f2(xw[1]); xv[2] = f1.x; xv[3] = f1.y; }
+            if constexpr (DM == 4) { const float2 f1 = io<T>::to_f2(nx_xw[1]); xv[2] = f1.x; xv[3] = f1.y; }
         }
         float x2 = 0.f;
 #pragma unroll
         for (int k = 0; k < DM; ++k) x2 = fmaf(xv[k], xv[k], x2);
         const float eps = (x2 + cmax_s[j]) * kEpsScale;
+        const bool has_next = i + 1 < n_items;
+        if (has_next) { advance(); fetch_x(); }      // operands of the next item are requested early
 
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-
-        // ---- epilogue: the 256 distances of my row, four chunks of 64 columns
         uint32_t cw[8];
         float mn[4];
+        // ---- half 0: columns 0..127
+        mbar_wait(bar0, i & 1);
+        tc_fence_after();
         float best = INFINITY;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
             float v[64];
             tmem_ld64(taddr + ch * 64, v);
             mn[ch] = reduce_chunk(v, best, eps, cw[2 * ch], cw[2 * ch + 1]);
             best = fminf(best, mn[ch]);
         }
+        if (has_next) build_and_issue_half0((i + 1) & 1);   // buffer 0 is free again: next item's first half starts now
+        // ---- half 1: columns 128..255
+        mbar_wait(bar1, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 2; ch < 4; ++ch) {
+            float v[64];
+            tmem_ld64(taddr + ch * 64, v);
+            mn[ch] = reduce_chunk(v, best, eps, cw[2 * ch], cw[2 * ch + 1]);
+            best = fminf(best, mn[ch]);
+        }
+        if (has_next) issue_half1((i + 1) & 1);
+
         int cnt = 0, code = 0;
 #pragma unroll
         for (int ch = 3; ch >= 0; --ch) {
@@ -264,12 +316,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a)
             const float* cm = a.cent + (int64_t)(m0 + j) * 256 * DM;
             float bestd = INFINITY;
             int bi = 0;
-            for (int i = 0; i < 8; ++i) {
-                uint32_t bits = cnt == 0 ? 0xffffffffu : cw[i];
+            for (int w = 0; w < 8; ++w) {
+                uint32_t bits = cnt == 0 ? 0xffffffffu : cw[w];
                 while (bits) {
                     const int lz = __clz(bits);
                     bits &= ~(0x80000000u >> lz);
-                    const int c = 32 * i + lz;
+                    const int c = 32 * w + lz;
                     float cv[DM];
 #pragma unroll
                     for (int k = 0; k < DM; ++k) cv[k] = __ldg(cm + c * DM + k);
@@ -357,7 +409,7 @@ int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C
 
 template <typename T, int DM>
 static int launch_tc_t(const tc::EncArgs& a, cudaStream_t stream) {
-    const size_t smem = tc::kMG * tc::kBTileBytes + 2 * tc::kATileBytes + tc::kZeroBytes + 16 + 16 + tc::kMG * 4 + 64;
+    const size_t smem = tc::kMG * tc::kBTileBytes + 4 * tc::kATileBytes + tc::kZeroBytes + 32 + 16 + tc::kMG * 4 + 64;
     static bool configured = false;
     if (!configured) {
         MILLION_CUDA_OK(cudaFuncSetAttribute(tc::encode_tc_kernel<T, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
