@@ -170,7 +170,11 @@ class PagedPQCache(DynamicPQCache):
         """Allocate pages for n_new_chunks more chunks: chunk-major, then b, then h (dynamic_paged_pq_utils.py:776-811)."""
         pm = self.page_managers[layer_idx]
         ids = pm.allocate_pages(n_new_chunks * self.bs * self.num_key_value_heads)
-        new = torch.tensor(ids, dtype=torch.int64).view(n_new_chunks, self.bs, self.num_key_value_heads).permute(1, 2, 0)
+        if ids[-1] - ids[0] == len(ids) - 1:      # the usual case: a consecutive run -> build the table slice on the device, no H2D copy
+            new = torch.arange(ids[0], ids[0] + len(ids), dtype=torch.int64, device=self.device)
+        else:
+            new = torch.tensor(ids, dtype=torch.int64)
+        new = new.view(n_new_chunks, self.bs, self.num_key_value_heads).permute(1, 2, 0)
         it = iter(ids)
         for _ in range(n_new_chunks):
             for b in range(self.bs):
