@@ -176,7 +176,7 @@ typedef struct million_attn_params {
 #define MILLION_ATTN_PARTIAL_ONLY 1
 
 /* Codebook preparation for the FAST decode-attention kernel: both codebooks as fp16 pairs in the kernel's gather
- * order (d=128, M=64, C=256 only: returns 0 bytes / MILLION_ERR_UNSUPPORTED otherwise).  One tiny launch; callers
+ * order (d=128, M in {32, 64}, C=256 only: returns 0 bytes / MILLION_ERR_UNSUPPORTED otherwise).  One tiny launch; callers
  * cache the result per codebook (DynamicPQCache.set_cent does). */
 int64_t million_pq_codebook_prepared_bytes(int d, int M, int C);
 int million_pq_codebook_prepare(const void* k_cent, const void* v_cent, int dtype, int d, int M, int C, void* prepared,

@@ -17,55 +17,10 @@
 //     the main loop; online softmax state is per warp and merged once at the end.
 //   * the fp16 window and the cross-CTA merge are fused (last split CTA / last-arrival ticket).
 // Replaces Interface.cu:49-118 + Kernel.cuh:11-166, 1038-1209, 1211-1270 of the reference.
-#include "attn_common.cuh"
+#include "attn_fast_helpers.cuh"
 
 namespace million {
 
-namespace fast {
-
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr int kTile = 32;                       // tokens per warp tile
-constexpr int kRowBytes = 64;                   // M = 64 one-byte codes
-constexpr int kStageBytes = 2 * kTile * kRowBytes;   // one K tile + one V tile per warp
-constexpr int kVtabBytes = 64 * 1024;
-constexpr int kFlatPad = 24;                    // cost of one more (prologue + epilogue) in 64-token units (~9 us)
-constexpr float kRescaleMargin = 6.f;           // log2 units: p <= 64 before a rescale is forced
-
-template <int G> struct LutCfg;
-template <> struct LutCfg<4> { static constexpr int bytes = 128 * 1024; };
-template <> struct LutCfg<2> { static constexpr int bytes = 64 * 1024; };
-template <> struct LutCfg<1> { static constexpr int bytes = 64 * 1024; };
-
-// column of sub-space m inside a 64-entry table row (both K tables and the V table)
-__host__ __device__ __forceinline__ constexpr int col_of(int m) {
-    const int W = m >> 2, b = m & 3;
-    return (b >> 1) * 32 + (b & 1) * 16 + W;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// plain shared-memory loads through the generic pointer of the dynamic smem block: the compiler is free to batch them
-// (asm volatile loads would be kept in program order and serialise on the 30-cycle LDS latency)
-__device__ __forceinline__ uint32_t lds32(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint32_t*>(base + off); }
-__device__ __forceinline__ uint2 lds64(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint2*>(base + off); }
-__device__ __forceinline__ uint4 lds128(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint4*>(base + off); }
-// acc_lo += fp16(packed.lo), acc_hi += fp16(packed.hi) in fp32: Blackwell FHADD (PTX add.rn.f32.f16), one op each
-__device__ __forceinline__ void fhadd2(float& acc_lo, float& acc_hi, uint32_t packed) {
-    const unsigned short lo = (unsigned short)(packed & 0xffffu), hi = (unsigned short)(packed >> 16);
-    asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc_lo) : "h"(lo));
-    asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc_hi) : "h"(hi));
-}
-__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
-__device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
-
-}  // namespace fast
 
 // ------------------------------------------------------------------------------------------------
 // Codebook preparation (once per codebook): fp16 tables in the column order the kernel gathers with.
@@ -92,44 +47,6 @@ int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, 
 }
 
 // ------------------------------------------------------------------------------------------------
-namespace fast {
-
-// Per-warp online-softmax state (uniform across the lanes of the warp) and accumulators.
-template <int G>
-struct WarpState {
-    float m[G];          // running max, log2 units (scaled logits)
-    float l[G];          // per-LANE partial denominator (summed across lanes at the end)
-    float o[4][G][2];    // per-lane fp32 output accumulators: slot s -> sub-space 4*l' + ((s + hw) & 3), 2 dims
-};
-
-template <int G>
-__device__ __forceinline__ void state_init(WarpState<G>& st) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) { st.m[g] = -INFINITY; st.l[g] = 0.f; }
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int g = 0; g < G; ++g) { st.o[b][g][0] = 0.f; st.o[b][g][1] = 0.f; }
-}
-
-// Table gathers with an absolute shared-window address: the PRMT result (code << 8 | column offset) is the register part,
-// the table base is an immediate, so a gather is exactly PRMT + LDS.  Not volatile: the tables are read-only in the main
-// loop and the compiler may schedule these loads freely.  kSmemBase is checked at kernel entry.
-constexpr uint32_t kSmemBase = 0x400;   // dynamic shared memory starts after the 1 KB the driver reserves per CTA (no static smem)
-template <uint32_t IMM>
-__device__ __forceinline__ uint2 gather64(uint32_t r) {
-    uint2 v;
-    asm("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(r), "n"(IMM));
-    return v;
-}
-template <uint32_t IMM>
-__device__ __forceinline__ uint32_t gather32(uint32_t r) {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(r), "n"(IMM));
-    return v;
-}
-
-}  // namespace fast
 
 // One segment = the coded tokens [t0, t1) of group (b, hk) (+ this CTA's share of the window), written as part `split` of
 // `np` parts of that group.
@@ -625,12 +542,16 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
     return MILLION_OK;
 }
 
+int launch_attn_fast_dm4(const AttnArgs& a, int io_dtype, int G, int gsub, const void* prepared, cudaStream_t stream);
+
 int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only) {
     AttnArgs a = a_in;
     a.n_parts = a.n_splits;   // the window is dealt out to the splits, no extra part
     a.flat = 0;
     const int Gfull = a.nh / a.nh_k;
-    if (a.d != 128 || a.M != 64 || a.C != 256) MILLION_UNSUPPORTED("fast decode attention needs d=128, M=64, C=256");
+    if (a.d != 128 || (a.M != 64 && a.M != 32) || a.C != 256) MILLION_UNSUPPORTED("fast decode attention needs d=128, M in {32, 64}, C=256");
+    const bool dm4 = a.M == 32;
+    if (dm4 && a.nk > 0 && a.v_layout != MILLION_V_ROWMAJOR) MILLION_UNSUPPORTED("fast decode attention, M=32: value codes must be row-major");
     if (!(Gfull == 1 || Gfull == 2 || Gfull % 4 == 0)) MILLION_UNSUPPORTED("fast decode attention needs nh/nh_k in {1,2,4k}");
     if (a.nk > 0 && a.v_layout == MILLION_V_PAGED && (a.page_size % 32 != 0 || ((uintptr_t)a.v_codes & 15)))
         MILLION_UNSUPPORTED("fast decode attention: paged V needs page_size %% 32 == 0 and an aligned pool");
@@ -662,6 +583,7 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
             a.flat = 1; a.flat_per = per; a.flat_ug = ug; a.n_parts = max_parts;
         }
     }
+    if (dm4) return launch_attn_fast_dm4(a, io_dtype, G, gsub, prepared, stream);
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
 #define MILLION_FAST_CASE(TT, GG) \
     return a.v_layout == MILLION_V_ROWMAJOR ? launch_fast_t<TT, GG, 0>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1>(a, prep, gsub, stream)

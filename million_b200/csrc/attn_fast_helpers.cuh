@@ -1,0 +1,93 @@
+// attn_fast_helpers.cuh — small device helpers shared by the fast decode-attention kernels (attn_fast.cu: M=64, d_m=2;
+// attn_fast_dm4.cu: M=32, d_m=4).
+#pragma once
+#include "attn_common.cuh"
+
+namespace million {
+
+namespace fast {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTile = 32;                       // tokens per warp tile
+constexpr int kRowBytes = 64;                   // M = 64 one-byte codes
+constexpr int kStageBytes = 2 * kTile * kRowBytes;   // one K tile + one V tile per warp
+constexpr int kVtabBytes = 64 * 1024;
+constexpr int kFlatPad = 24;                    // cost of one more (prologue + epilogue) in 64-token units (~9 us)
+constexpr float kRescaleMargin = 6.f;           // log2 units: p <= 64 before a rescale is forced
+
+template <int G> struct LutCfg;
+template <> struct LutCfg<4> { static constexpr int bytes = 128 * 1024; };
+template <> struct LutCfg<2> { static constexpr int bytes = 64 * 1024; };
+template <> struct LutCfg<1> { static constexpr int bytes = 64 * 1024; };
+
+// column of sub-space m inside a 64-entry table row (both K tables and the V table)
+__host__ __device__ __forceinline__ constexpr int col_of(int m) {
+    const int W = m >> 2, b = m & 3;
+    return (b >> 1) * 32 + (b & 1) * 16 + W;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// plain shared-memory loads through the generic pointer of the dynamic smem block: the compiler is free to batch them
+// (asm volatile loads would be kept in program order and serialise on the 30-cycle LDS latency)
+__device__ __forceinline__ uint32_t lds32(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint32_t*>(base + off); }
+__device__ __forceinline__ uint2 lds64(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint2*>(base + off); }
+__device__ __forceinline__ uint4 lds128(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const uint4*>(base + off); }
+// acc_lo += fp16(packed.lo), acc_hi += fp16(packed.hi) in fp32: Blackwell FHADD (PTX add.rn.f32.f16), one op each
+__device__ __forceinline__ void fhadd2(float& acc_lo, float& acc_hi, uint32_t packed) {
+    const unsigned short lo = (unsigned short)(packed & 0xffffu), hi = (unsigned short)(packed >> 16);
+    asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc_lo) : "h"(lo));
+    asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc_hi) : "h"(hi));
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+}  // namespace fast
+
+namespace fast {
+
+// Per-warp online-softmax state (uniform across the lanes of the warp) and accumulators.
+template <int G>
+struct WarpState {
+    float m[G];          // running max, log2 units (scaled logits)
+    float l[G];          // per-LANE partial denominator (summed across lanes at the end)
+    float o[4][G][2];    // per-lane fp32 output accumulators: slot s -> sub-space 4*l' + ((s + hw) & 3), 2 dims
+};
+
+template <int G>
+__device__ __forceinline__ void state_init(WarpState<G>& st) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) { st.m[g] = -INFINITY; st.l[g] = 0.f; }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) { st.o[b][g][0] = 0.f; st.o[b][g][1] = 0.f; }
+}
+
+// Table gathers with an absolute shared-window address: the PRMT result (code << 8 | column offset) is the register part,
+// the table base is an immediate, so a gather is exactly PRMT + LDS.  Not volatile: the tables are read-only in the main
+// loop and the compiler may schedule these loads freely.  kSmemBase is checked at kernel entry.
+constexpr uint32_t kSmemBase = 0x400;   // dynamic shared memory starts after the 1 KB the driver reserves per CTA (no static smem)
+template <uint32_t IMM>
+__device__ __forceinline__ uint2 gather64(uint32_t r) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(r), "n"(IMM));
+    return v;
+}
+template <uint32_t IMM>
+__device__ __forceinline__ uint32_t gather32(uint32_t r) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(r), "n"(IMM));
+    return v;
+}
+
+}  // namespace fast
+
+}  // namespace million

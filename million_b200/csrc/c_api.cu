@@ -36,6 +36,7 @@ int sm_count() {
 int launch_attn_generic(const AttnArgs& a, int io_dtype, cudaStream_t stream);
 int launch_attn_fast(const AttnArgs& a, int io_dtype, const void* prepared, cudaStream_t stream, bool probe_only);
 int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, void* out, cudaStream_t stream);
+int launch_codebook_prepare_dm4(const void* kcent, const void* vcent, int io_dtype, void* out, cudaStream_t stream);
 int launch_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, cudaStream_t stream);
 int launch_reconstruct(const void* codes, int code_bytes, int64_t chs, int64_t cts, int64_t cms, const void* cent, void* out,
                        int dtype, int64_t ohs, int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream);
@@ -127,13 +128,14 @@ int million_pq_decode(const void* codes, int code_bytes, int64_t chs, int64_t ct
                               (cudaStream_t)stream);
 }
 
-int64_t million_pq_codebook_prepared_bytes(int d, int M, int C) { return (d == 128 && M == 64 && C == 256) ? 2 * 64 * 256 * 4 : 0; }
+int64_t million_pq_codebook_prepared_bytes(int d, int M, int C) { return (d == 128 && (M == 64 || M == 32) && C == 256) ? 2 * 64 * 1024 : 0; }
 
 int million_pq_codebook_prepare(const void* k_cent, const void* v_cent, int dtype, int d, int M, int C, void* prepared,
                                 million_stream_t stream) {
     MILLION_REQUIRE(k_cent && v_cent && prepared, "codebook_prepare: null pointer");
     MILLION_REQUIRE(dtype >= MILLION_F16 && dtype <= MILLION_F32, "codebook_prepare: bad dtype");
-    if (million_pq_codebook_prepared_bytes(d, M, C) == 0) MILLION_UNSUPPORTED("codebook_prepare: only d=128, M=64, C=256");
+    if (million_pq_codebook_prepared_bytes(d, M, C) == 0) MILLION_UNSUPPORTED("codebook_prepare: only d=128, M in {32, 64}, C=256");
+    if (M == 32) return launch_codebook_prepare_dm4(k_cent, v_cent, dtype, prepared, (cudaStream_t)stream);
     return launch_codebook_prepare(k_cent, v_cent, dtype, prepared, (cudaStream_t)stream);
 }
 

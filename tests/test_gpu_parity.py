@@ -288,3 +288,15 @@ def test_full_size_llama31_8b_32k_properties(M):
     out2 = M.pq_decode_attn(q, kc, vc, kcent, vcent, kres, vres, 0)
     want = vcent[:, 7, :].reshape(1, 1, 1, d).float().expand(bs, nh, 1, d)
     torch.testing.assert_close(out2.float(), want, atol=ATOL, rtol=RTOL)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bs,nh,nh_k,nk,r", [(1, 32, 8, 5000, 128), (2, 8, 8, 777, 17), (1, 16, 8, 64, 1), (1, 32, 4, 2100, 40), (2, 4, 4, 0, 9)])
+def test_attn_two_bit_config_fast_path(M, dtype, bs, nh, nh_k, nk, r):
+    """M=32, d_m=4 ('2-bit', BASELINE config 5): the dedicated fast kernel (attn_fast_dm4.cu) against the oracle."""
+    from million_b200 import _lib as L
+    inp, t = _rand_case(bs, nh, nh_k, nk, r, Mm=32, seed=bs + nh + nk, dtype=dtype)
+    out = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=L.IMPL_FAST)
+    f = lambda k: t[k].float().cpu().numpy()
+    ref = O.pq_decode_attn(f("q"), inp["kc"], inp["vc"], f("kcent"), f("vcent"), f("kres"), f("vres"), r)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=ATOL if dtype == torch.float16 else 8e-3, rtol=RTOL)
