@@ -129,3 +129,48 @@ def test_synthetic_token_perplexity_parity():
     nll_gpu = run(lambda q, k, v, l: cache.prefill(q.cuda(), k.cuda(), v.cuda(), l, distort_recent=True).float().cpu())
     nll_ref = run(lambda q, k, v, l: torch.from_numpy(oracle.prefill(q.numpy(), k.numpy(), v.numpy(), l, distort_recent=True)))
     assert abs(np.exp(nll_gpu) / np.exp(nll_ref) - 1) < 5e-3
+
+
+@pytest.mark.parametrize("dtype,bs,nh,nh_k,M", [(torch.bfloat16, 2, 8, 2, 64), (torch.float16, 2, 4, 4, 32), (torch.float16, 1, 16, 2, 64)])
+def test_dynamic_cache_batched_gqa_bf16(dtype, bs, nh, nh_k, M):
+    """bs > 1 (the reference hard-wires 1, pq_utils.py:56), GQA 4 and 8, bf16, the 2-bit shape: prefill + decode across a flush."""
+    from million_b200.pq_utils import DynamicPQCache
+    kw = dict(bs=bs, nh=nh, num_key_value_heads=nh_k, M=M, layer_num=2, d=128)
+    rng = np.random.default_rng(5)
+    mk = lambda *s: torch.from_numpy(rng.standard_normal(s, dtype=np.float32)).to(dtype)
+    kc, vc = mk(M, 256, 128 // M), mk(M, 256, 128 // M)
+    cache = _mk(DynamicPQCache, scalar_t=dtype, **kw)
+    cache.set_cent(kc.cuda(), vc.cuda())
+    oracle = O.DynamicPQCacheOracle(**kw)
+    oracle.set_cent(kc.float().numpy(), vc.float().numpy())
+    atol = ATOL if dtype == torch.float16 else 8e-3
+    for layer in (0, 1):
+        q, k, v = mk(bs, nh, 70, 128), mk(bs, nh_k, 70, 128), mk(bs, nh_k, 70, 128)
+        out = cache.prefill(q.cuda(), k.cuda(), v.cuda(), layer)
+        ref = oracle.prefill(q.float().numpy(), k.float().numpy(), v.float().numpy(), layer)
+        np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=2 * atol, rtol=RTOL)
+    for step in range(135):
+        for layer in (0, 1):
+            q, k, v = mk(bs, nh, 1, 128), mk(bs, nh_k, 1, 128), mk(bs, nh_k, 1, 128)
+            out = cache.decoding(q.cuda(), k.cuda(), v.cuda(), layer)
+            ref = oracle.decoding(q.float().numpy(), k.float().numpy(), v.float().numpy(), layer)
+            np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=atol, rtol=RTOL, err_msg=f"step {step} layer {layer}")
+    assert cache.key_cache[1].shape == (bs, nh_k, 70 + 128, M) and cache.residualed_tokens == [7, 7]
+    assert np.array_equal(cache.key_cache[0].cpu().numpy(), oracle.key_cache[0])
+    assert np.array_equal(cache.value_cache[1].cpu().numpy(), oracle.value_cache[1])
+
+
+def test_errors_are_exceptions_not_exit():
+    """The reference prints and exit()s on a launch error (Interface.cu:3-11); here bad arguments raise MillionError."""
+    from million_b200 import _lib as L, ops
+    q = torch.randn(1, 8, 1, 128, device="cuda").half()
+    kc = torch.zeros(1, 2, 10, 64, dtype=torch.uint8, device="cuda")
+    cent = torch.randn(64, 256, 2, device="cuda").half()
+    res = torch.randn(1, 2, 128, 128, device="cuda").half()
+    with pytest.raises(L.MillionError, match="r"):
+        ops.pq_decode_attn(q, kc, kc, cent, cent, res, res, 200)            # r > window length
+    with pytest.raises(L.MillionError):
+        ops.pq_decode_attn(q, kc, kc, cent, cent, res, res, 5, impl=L.IMPL_FAST, prepared=None, v_layout=L.V_PAGED,
+                           v_page_ids=torch.zeros(1, 2, 0, dtype=torch.int64, device="cuda"), page_size=64)   # 0 pages for 10 tokens
+    out = ops.pq_decode_attn(q, kc, kc, cent, cent, res, res, 5)           # the library is still usable afterwards
+    assert torch.isfinite(out).all()
