@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MILLION_ABI_VERSION 3
+#define MILLION_ABI_VERSION 4
 
 typedef void* million_stream_t; /* cudaStream_t */
 
@@ -191,6 +191,15 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
  * Same algebra as flash_decoding_reduce_kernel (Kernel.cuh:1249-1269); empty parts (l = 0) are skipped. */
 int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype,
                       million_stream_t stream);
+
+/* Split-KV across GPUs without a collective library: every rank stores its partial state into the slot it owns in every
+ * peer's symmetric buffer (NVLink P2P stores), publishes a flag, waits for all sources and merges — one launch, graph
+ * capturable.  `peer_bases_host`: host array of `world` device pointers, the symmetric buffers of all ranks mapped into
+ * this process (e.g. torch.distributed._symmetric_memory buffer_ptrs), each million_splitkv_symmetric_bytes() big and
+ * zero-initialised once.  `state`: 16 bytes of zero-initialised device memory private to this rank. */
+int64_t million_splitkv_symmetric_bytes(int world, int64_t rows, int d);
+int million_splitkv_push_merge(const float* local_partial, void* const* peer_bases_host, int rank, int world, int64_t rows, int d,
+                               void* out, int io_dtype, void* state, million_stream_t stream);
 
 /* window[(head), r0 + i, :] = src[(head), i, :] for i < n — pq_utils.py:304-311, paged_pq_utils.py:377-378.
  * Both K and V in one launch.  Strides in ELEMENTS. */

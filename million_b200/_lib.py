@@ -13,7 +13,7 @@ MILLION_OK, MILLION_ERR_INVALID, MILLION_ERR_UNSUPPORTED, MILLION_ERR_CUDA = 0, 
 V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_FAST = 0, 1, 2
 ATTN_PARTIAL_ONLY = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
 
@@ -58,6 +58,8 @@ SIGNATURES = {
     "million_pq_decode_attn_default_splits": (ctypes.c_int, [ctypes.c_int] * 3),
     "million_pq_decode_attn": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),
     "million_lse_merge": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
+    "million_splitkv_symmetric_bytes": (c_i64, [ctypes.c_int, c_i64, ctypes.c_int]),
+    "million_splitkv_push_merge": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp]),
     "million_window_append": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, c_vp]),
     "million_window_shift": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

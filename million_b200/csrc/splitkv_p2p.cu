@@ -1,0 +1,144 @@
+// splitkv_p2p.cu — cross-GPU merge of split-KV partial states over NVLink peer memory, fused into ONE small kernel:
+// every rank stores its (rows, d+2) fp32 state [o un-normalised | m | l] straight into the receive slot it owns in every
+// peer's symmetric buffer (P2P stores), publishes a sequence flag with release semantics at system scope, waits for the
+// flags of all sources and applies the log-sum-exp merge (flash_decoding_reduce_kernel algebra,
+// scripts/modeldb/bindings/Kernel.cuh:1249-1269).  Replaces NCCL all_gather + merge (2 launches + ~15 us of collective
+// latency per layer) and, unlike NCCL on this pool, can be captured in a CUDA graph: the sequence number lives in device
+// memory.  The reference has no multi-GPU path (scripts/modeldb/main_pq.py:74).
+//
+// Symmetric buffer of every rank (same layout everywhere):
+//   [0, 1024)        flags: flag of source rank g at byte 128*g (uint32 sequence number, monotonically increasing)
+//   [1024, ...)      recv[parity 2][world][rows][d+2] fp32
+// Double buffering by sequence parity is enough: a rank can publish call n+1 only after it finished call n (stream order),
+// and a peer can start call n+2 only after it has seen everybody's call n+1.
+#include "common.cuh"
+
+namespace million {
+
+constexpr int kMaxWorld = 8;
+struct P2PArgs {
+    unsigned char* peer[kMaxWorld];   // symmetric buffer of every rank, mapped into this process
+    const float* local;               // (rows, d+2) this rank's state
+    void* out;                        // (rows, d)
+    unsigned* counter;                // device: calls completed so far
+    int* ticket;                      // device: zero between launches
+    int* err;                         // device: set to 1 if a wait timed out
+    int64_t rows;
+    int rank, world, d;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) splitkv_push_merge_kernel(const P2PArgs a) {
+    __shared__ unsigned seq_s;
+    __shared__ float wts[kMaxWorld], hd[2];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, stride = a.d + 2;
+    if (tid == 0) seq_s = *reinterpret_cast<volatile unsigned*>(a.counter) + 1;
+    __syncthreads();
+    const unsigned seq = seq_s, par = seq & 1;
+    const size_t slot_floats = (size_t)a.rows * stride;
+
+    // ---- push my row into slot [par][rank] of every rank (my own included)
+    const float* src = a.local + row * stride;
+    for (int g = 0; g < a.world; ++g) {
+        float* dst = reinterpret_cast<float*>(a.peer[g] + 1024) + ((size_t)par * a.world + a.rank) * slot_floats + row * stride;
+        for (int i = tid; i < stride; i += blockDim.x) dst[i] = src[i];
+    }
+    // Ordering: my block's stores -> bar.sync -> acq_rel ticket at gpu scope -> (last block) release stores of the flags at
+    // system scope -> the peers' acquire loads.  Causality is transitive across the two scopes, so no per-thread system fence.
+    __shared__ int is_last;
+    __syncthreads();
+    if (tid == 0) {
+        int t;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(a.ticket) : "memory");
+        is_last = (t == (int)gridDim.x - 1);
+        if (is_last) {
+            *a.ticket = 0;
+            *reinterpret_cast<volatile unsigned*>(a.counter) = seq;
+        }
+    }
+    __syncthreads();
+    if (is_last && tid < a.world) st_release_sys(reinterpret_cast<unsigned*>(a.peer[tid] + 128 * a.rank), seq);   // every block of this rank has pushed
+    // ---- wait for the state of every source rank (bounded: a dead peer must not hang the GPU)
+    if (tid < a.world) {
+        const unsigned* f = reinterpret_cast<const unsigned*>(a.peer[a.rank] + 128 * tid);
+        int spins = 0;
+        while ((int)(ld_acquire_sys(f) - seq) < 0) {
+            __nanosleep(100);
+            if (++spins > (1 << 23)) { *a.err = 1; break; }
+        }
+    }
+    __syncthreads();
+
+    // ---- merge
+    const float* base = reinterpret_cast<const float*>(a.peer[a.rank] + 1024) + (size_t)par * a.world * slot_floats + row * stride;
+    if (tid == 0) {
+        float mstar = -INFINITY;
+        for (int g = 0; g < a.world; ++g) {
+            const float* p = base + (size_t)g * slot_floats;
+            if (__ldcg(p + a.d + 1) > 0.f) mstar = fmaxf(mstar, __ldcg(p + a.d));
+        }
+        float den = 0.f;
+        for (int g = 0; g < a.world; ++g) {
+            const float* p = base + (size_t)g * slot_floats;
+            const float l = __ldcg(p + a.d + 1);
+            const float w = l > 0.f ? __expf(__ldcg(p + a.d) - mstar) : 0.f;
+            wts[g] = w;
+            den += l * w;
+        }
+        hd[0] = den;
+    }
+    __syncthreads();
+    const float den = hd[0];
+    for (int k = tid; k < a.d; k += blockDim.x) {
+        float acc = 0.f;
+        for (int g = 0; g < a.world; ++g) acc = fmaf(__ldcg(base + (size_t)g * slot_floats + k), wts[g], acc);
+        reinterpret_cast<T*>(a.out)[row * a.d + k] = io<T>::from_f(den > 0.f ? acc / den : 0.f);
+    }
+}
+
+int launch_splitkv_push_merge(const P2PArgs& a, int io_dtype, cudaStream_t stream) {
+    if (a.rows == 0) return MILLION_OK;
+    dim3 grid((unsigned)a.rows), block(128);
+    if (io_dtype == MILLION_F16) splitkv_push_merge_kernel<__half><<<grid, block, 0, stream>>>(a);
+    else if (io_dtype == MILLION_BF16) splitkv_push_merge_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(a);
+    else splitkv_push_merge_kernel<float><<<grid, block, 0, stream>>>(a);
+    MILLION_CUDA_OK(cudaGetLastError());
+    return MILLION_OK;
+}
+
+}  // namespace million
+
+using namespace million;
+
+extern "C" {
+
+int64_t million_splitkv_symmetric_bytes(int world, int64_t rows, int d) {
+    return 1024 + (int64_t)2 * world * rows * (d + 2) * 4;
+}
+
+/* state: device memory of 16 bytes, zero-initialised by the caller once: [counter u32 | ticket i32 | err i32 | pad] */
+int million_splitkv_push_merge(const float* local_partial, void* const* peer_bases_host, int rank, int world, int64_t rows, int d,
+                               void* out, int io_dtype, void* state, million_stream_t stream) {
+    MILLION_REQUIRE(local_partial && peer_bases_host && out && state, "splitkv_push_merge: null pointer");
+    MILLION_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "splitkv_push_merge: world must be 1..8");
+    MILLION_REQUIRE(rows >= 0 && rows < (1ll << 31) && d > 0, "splitkv_push_merge: bad sizes");
+    MILLION_REQUIRE(io_dtype >= MILLION_F16 && io_dtype <= MILLION_F32, "splitkv_push_merge: bad dtype");
+    P2PArgs a;
+    for (int g = 0; g < kMaxWorld; ++g) a.peer[g] = g < world ? (unsigned char*)peer_bases_host[g] : nullptr;
+    a.local = local_partial; a.out = out;
+    a.counter = (unsigned*)state; a.ticket = (int*)state + 1; a.err = (int*)state + 2;
+    a.rows = rows; a.rank = rank; a.world = world; a.d = d;
+    return launch_splitkv_push_merge(a, io_dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -59,3 +59,50 @@ def splitkv_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, 
     attn_fn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, partial=partial, **attn_kw)
     parts = allgather_partials(partial, group)
     return merge_fn(parts, d, q.dtype).view(bs, nh, 1, d)
+
+
+class SplitKVPeerGroup:
+    """Split-KV decode attention whose cross-GPU exchange is the library's own NVLink kernel (million_splitkv_push_merge)
+    instead of NCCL: partial states are stored directly into the peers' symmetric buffers and merged in the same launch.
+    Symmetric memory comes from torch.distributed._symmetric_memory (CUDA IPC / fabric handles); torch is plumbing only."""
+
+    def __init__(self, rows, d, dtype, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.rows, self.d, self.dtype = rows, d, dtype
+        nbytes = L.lib().million_splitkv_symmetric_bytes(self.world, rows, d)
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, self.group)
+        ptrs = list(self.handle.buffer_ptrs)
+        self._peer_array = (ctypes.c_void_p * self.world)(*ptrs)
+        self.state = torch.zeros(4, dtype=torch.int32, device=self.buf.device)
+        self.partial = torch.empty(rows, d + 2, dtype=torch.float32, device=self.buf.device)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+
+    def merge(self, out=None):
+        """Push self.partial to every rank and merge everybody's state; returns (rows, d)."""
+        import ctypes
+        from . import _lib as L
+        from .ops import _DT
+        if out is None:
+            out = torch.empty(self.rows, self.d, dtype=self.dtype, device=self.buf.device)
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)
+        L.check(L.lib().million_splitkv_push_merge(ctypes.c_void_p(self.partial.data_ptr()), ctypes.cast(self._peer_array, ctypes.c_void_p),
+                                                   self.rank, self.world, self.rows, self.d, ctypes.c_void_p(out.data_ptr()), _DT[self.dtype],
+                                                   ctypes.c_void_p(self.state.data_ptr()), st))
+        return out
+
+    def decode_attn(self, q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, out=None, **attn_kw):
+        from . import ops
+        bs, nh, d = q.shape[0], q.shape[1], q.shape[-1]
+        ops.pq_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, partial=self.partial, **attn_kw)
+        o = self.merge(None if out is None else out.view(bs * nh, d))
+        return o.view(bs, nh, 1, d)
+
+    def timed_out(self):
+        return bool(self.state[2].item())

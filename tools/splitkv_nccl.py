@@ -7,7 +7,7 @@ import torch, torch.distributed as dist
 from million_b200 import ops, sharding
 
 ap = argparse.ArgumentParser(); ap.add_argument("--ctx", type=int, default=131072); ap.add_argument("--layers", type=int, default=32)
-ap.add_argument("--steps", type=int, default=20); ap.add_argument("--graph", action="store_true"); a = ap.parse_args()
+ap.add_argument("--steps", type=int, default=20); ap.add_argument("--graph", action="store_true"); ap.add_argument("--p2p", action="store_true"); a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1: dist.init_process_group("nccl", device_id=dev)
@@ -23,20 +23,25 @@ s, e = sharding.split_kv_ranges(nk, world)[rank]
 kcl, vcl = kc[:, :, s:e].contiguous(), vc[:, :, s:e].contiguous()
 r_local = r if rank == world - 1 else 0
 full = ops.pq_decode_attn(q, kc, vc, kcent, vcent, kres, vres, r)
-if world > 1:
+peer = sharding.SplitKVPeerGroup(NH, D, torch.float16) if (a.p2p and world > 1) else None
+if peer is not None:
+    out = peer.decode_attn(q, kcl, vcl, kcent, vcent, kres, vres, r_local).clone()
+elif world > 1:
     out = sharding.splitkv_decode_attn(q, kcl, vcl, kcent, vcent, kres, vres, r_local)
 else:
     out = full
 err = (out.float() - full.float()).abs().max().item()
 # timing: `layers` calls per step (per-layer slices of the same size), device events, max over ranks
 layers = [(kcl.clone(), vcl.clone()) for _ in range(min(a.layers, 8))]
+outbuf = torch.empty(1, NH, 1, D, dtype=torch.float16, device=dev)
 def step():
     for i in range(a.layers):
         k_, v_ = layers[i % len(layers)]
-        if world > 1: sharding.splitkv_decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local)
+        if peer is not None: peer.decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, out=outbuf)
+        elif world > 1: sharding.splitkv_decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local)
         else: ops.pq_decode_attn(q, k_, v_, kcent, vcent, kres, vres, r)
 for _ in range(3): step()
-if a.graph and world == 1:   # NCCL collectives inside a captured graph hung on this pool (driver 580 / NCCL 2.28): single rank only
+if a.graph and (world == 1 or peer is not None):   # NCCL collectives inside a captured graph hung on this pool; the P2P kernel is plain launches
     # capture the whole 32-layer step (kernels + NCCL all-gathers + merges) in one CUDA graph: no per-layer launch cost
     torch.cuda.synchronize()
     st = torch.cuda.Stream()
@@ -58,8 +63,23 @@ for _ in range(a.steps): step()
 e1.record(); torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if peer is not None:
+    # the exchange alone: push + flag + wait + merge of a fixed partial state
+    for _ in range(5): peer.merge(outbuf.view(NH, D))
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(200): peer.merge(outbuf.view(NH, D))
+    e1.record(); torch.cuda.synchronize()
+    tm = torch.tensor([e0.elapsed_time(e1) / 200 * 1e3], device=dev); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    # the local attention alone (partial only)
+    e0.record()
+    for _ in range(50):
+        for k_, v_ in layers: ops.pq_decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, partial=peer.partial)
+    e1.record(); torch.cuda.synchronize()
+    ta = torch.tensor([e0.elapsed_time(e1) / (50 * len(layers)) * 1e3], device=dev); dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+    if rank == 0: print(f"  exchange+merge kernel alone: {tm.item():.1f} us per call (eager launches); local partial attention alone: {ta.item():.1f} us per layer")
 if rank == 0:
     ms = t.item(); alg = 2 * NHK * nk * M + 2 * NHK * r * D * 2
-    print(f"split-KV world={world} ctx={a.ctx} graph={a.graph}: max|merged - single| = {err:.2e}; {ms:.3f} ms per {a.layers}-layer token -> {1e3/ms:.1f} tok/s; "
+    print(f"split-KV world={world} ctx={a.ctx} graph={a.graph} p2p={a.p2p} timed_out={peer.timed_out() if peer is not None else None}: max|merged - single| = {err:.2e}; {ms:.3f} ms per {a.layers}-layer token -> {1e3/ms:.1f} tok/s; "
           f"{alg * a.layers / (ms * 1e-3) / 1e9:.0f} GB/s aggregate algorithmic")
 if world > 1: dist.destroy_process_group()
