@@ -297,6 +297,13 @@ class PagedPQCache(DynamicPQCache):
             self.flush_to_pages(layer_idx)
         r = self.residualed_tokens[layer_idx]
         n = key_states.size(2)
+        if (n == 1 and self.nbits == 8 and query_states.dtype == self.scalar_t and key_states.dtype == self.scalar_t
+                and query_states.is_contiguous() and key_states.is_contiguous() and value_states.is_contiguous()):
+            self._stats['paged_kernel_calls'] += 1
+            out = self._decode_fast(query_states, key_states, value_states, layer_idx, r)    # same two C calls, pre-filled params
+            if self.async_flush and self.residualed_tokens[layer_idx] >= self.extended_residual_size:
+                self._start_async_flush(layer_idx, self.page_size)
+            return out
         ops.window_append(self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], key_states, value_states, r)
         self.residualed_tokens[layer_idx] += n
         self.seen_tokens[layer_idx] += n          # each token counted once (the reference double-counts, Appendix B.5)
@@ -306,6 +313,11 @@ class PagedPQCache(DynamicPQCache):
         return out
 
     decoding = decoding_with_pages
+
+    def _fill_v(self, p, layer_idx):
+        tab = self._table[layer_idx]
+        p.v_layout, p.v_codes = L.V_PAGED, self.page_managers[layer_idx].page_pool.data_ptr()
+        p.v_page_ids, p.n_pages, p.page_size = tab.data_ptr(), tab.shape[2], self.page_size
 
     def _call_paged_kernel(self, query_states, layer_idx, residual_length):
         """paged_pq_utils.py:399-681 — the 13-argument paged kernel call, for every (b, h) (the reference builds

@@ -377,6 +377,13 @@ class DynamicPQCache(metaclass=Singleton):
 
         r = self.residualed_tokens[layer_idx]
         n = key_states.size(2)
+        if (n == 1 and self.nbits == 8 and query_states.dtype == self.scalar_t and key_states.dtype == self.scalar_t
+                and query_states.is_contiguous() and key_states.is_contiguous() and value_states.is_contiguous()
+                and type(self)._fast_decode_ok):
+            out = self._decode_fast(query_states, key_states, value_states, layer_idx, r)
+            if self.async_flush and self.residualed_tokens[layer_idx] == self.max_residual_length:
+                self._start_async_flush(layer_idx, self.max_residual_length)
+            return out
         ops.window_append(self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], key_states, value_states, r)
         self.residualed_tokens[layer_idx] += n
         self.seen_tokens[layer_idx] += n
@@ -388,6 +395,60 @@ class DynamicPQCache(metaclass=Singleton):
                      self.residualed_tokens[layer_idx])
         if self.async_flush and self.residualed_tokens[layer_idx] == self.max_residual_length:
             self._start_async_flush(layer_idx, self.max_residual_length)
+        return out
+
+    # ---- the same two C-ABI calls (window append + attention) without the Python layers in between
+    _fast_decode_ok = True
+
+    def _fill_v(self, p, layer_idx):
+        vs = self._v[layer_idx]
+        p.v_layout, p.v_codes, p.v_head_stride = L.V_ROWMAJOR, vs.buf.data_ptr(), vs.cap * self.M
+
+    def _decode_fast(self, q, k, v, layer_idx, r):
+        """One decode step of one layer: exactly what decoding() does through KernelRegistry -> bindings -> ops, but with a
+        per-layer, pre-filled million_attn_params (the per-call Python work is what bounds batch-1 decode)."""
+        import ctypes
+        plans = self.__dict__.setdefault('_plans', {})
+        plan = plans.get(layer_idx)
+        kc, vc = self._attn_cents(q.dtype)
+        if plan is None or plan['cent'] is not kc:
+            lib = L.lib()
+            p = L.AttnParams()
+            p.struct_size = ctypes.sizeof(L.AttnParams)
+            p.io_dtype = ops._DT[q.dtype]
+            p.impl, p.flags = L.IMPL_AUTO, 0
+            p.bs, p.nh, p.nh_k, p.d, p.M, p.C = self.bs, self.nh, self.num_key_value_heads, self.d, self.M, kc.shape[1]
+            p.v_layout = L.V_ROWMAJOR
+            p.k_cent, p.v_cent = kc.data_ptr(), vc.data_ptr()
+            p.k_res, p.v_res = self.key_residual_cache[layer_idx].data_ptr(), self.value_residual_cache[layer_idx].data_ptr()
+            p.res_len = self.max_residual_length
+            prepared = ops.prepare_codebooks(kc, vc)
+            if prepared is not None:
+                p.prepared_codebook = prepared.data_ptr()
+            max_splits = ops.default_splits(self.bs, self.num_key_value_heads, 1 << 30)
+            ws = ops.attn_workspace(q.device, self.bs, self.nh, self.num_key_value_heads, self.d, max_splits)
+            p.workspace, p.workspace_bytes, p.n_splits = ws.data_ptr(), ws.numel(), 0
+            plan = dict(p=p, ref=ctypes.byref(p), cent=kc, keep=(prepared, ws, vc), attn=lib.million_pq_decode_attn,
+                        append=lib.million_window_append, heads=self.bs * self.num_key_value_heads,
+                        win=(ctypes.c_void_p(p.k_res), ctypes.c_void_p(p.v_res)), dt=ops._DT[q.dtype])
+            plans[layer_idx] = plan
+        p = plan['p']
+        stream = ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+        st = plan['append'](plan['win'][0], plan['win'][1], self.max_residual_length * self.d, ctypes.c_void_p(k.data_ptr()),
+                            ctypes.c_void_p(v.data_ptr()), self.d, plan['heads'], r, 1, self.d, plan['dt'], stream)
+        if st:
+            L.check(st)
+        self.residualed_tokens[layer_idx] = r + 1
+        self.seen_tokens[layer_idx] += 1
+        ks = self._k[layer_idx]
+        out = torch.empty(self.bs, self.nh, 1, self.d, dtype=q.dtype, device=q.device)
+        p.q, p.out, p.nk, p.r = q.data_ptr(), out.data_ptr(), ks.len, r + 1
+        if ks.len:
+            p.k_codes, p.k_head_stride = ks.buf.data_ptr(), ks.cap * self.M
+            self._fill_v(p, layer_idx)
+        st = plan['attn'](plan['ref'], stream)
+        if st:
+            L.check(st)
         return out
 
     # ---- size properties (pq_utils.py:383-408)
