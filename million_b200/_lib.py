@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmillion_b200.so")
+# MILLION_B200_LIB: development override (A/B runs of two builds on the same box); the default is the in-tree build
+LIB_PATH = os.environ.get("MILLION_B200_LIB") or os.path.join(HERE, "libmillion_b200.so")
 
 MILLION_F16, MILLION_BF16, MILLION_F32 = 0, 1, 2
 MILLION_OK, MILLION_ERR_INVALID, MILLION_ERR_UNSUPPORTED, MILLION_ERR_CUDA = 0, 1, 2, 3

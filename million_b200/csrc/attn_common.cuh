@@ -29,17 +29,19 @@ struct AttnArgs {
     int flat, flat_per, flat_ug;   // flat scheduling: CTA c owns 64-token units [c*flat_per, (c+1)*flat_per) of the (group, unit) space
     int units_per_split;  // 16-token units per split
     float scale_log2;     // log2(e)/sqrt(d)
-    unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 8 globaltimer stamps per CTA
+    int dbg_mode;                     // hidden ablation switch (million_debug_set_mode): bit 0 skips QK gathers, bit 1 skips PV
+    unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 64 words per CTA, see dbg_stamp
 };
 
-__device__ __forceinline__ void dbg_stamp(const AttnArgs& a, int slot) {
-    if (a.dbg_timing && threadIdx.x == 0) {
+// 64 words per CTA: raw globaltimer stamps [piece 0..3][slot 0..15] (stores only: a stamp must not wait on memory)
+__device__ __forceinline__ void dbg_stamp(unsigned long long* dbg_timing, int piece, int slot) {
+    if (dbg_timing && threadIdx.x == 0 && piece < 4) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        a.dbg_timing[cta * 8 + slot] = t;
+        dbg_timing[(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 64 + piece * 16 + slot] = t;
     }
 }
+__device__ __forceinline__ void dbg_stamp(const AttnArgs& a, int slot, int piece = 0) { dbg_stamp(a.dbg_timing, piece, slot); }
 
 // tokens [begin, end) of split `s`
 __device__ __forceinline__ void split_range(const AttnArgs& a, int s, int& begin, int& end) {
@@ -64,8 +66,21 @@ __device__ __forceinline__ int v_code_at(const AttnArgs& a, int hb, int j, int m
 // round trips per head and per part used to put 10 us on the tail of every batch-1 launch.
 // `scr` = shared scratch of kMergeScratch floats.
 constexpr int kMergeScratch = 3 * 2048 + 64;
+struct MergeArgs {
+    int nh, nh_k, n_parts, d;
+    const float* parts;
+    float* partial_out;
+    void* out;
+    float* big;            // optional large shared staging buffer lent by the caller (dead tables), big_floats floats
+    int big_floats;
+    unsigned long long* dbg_timing;
+    int dbg_piece;
+};
+__device__ __forceinline__ void dbg_stamp_m(const MergeArgs& a, int slot) { dbg_stamp(a.dbg_timing, a.dbg_piece, slot); }
+// Out of line on purpose: it runs once per group, and inlined into the attention kernels its registers and code perturb the
+// allocation and layout of their main loops (measured: +7 us per launch at batch 8 for the same loop rate).
 template <typename T>
-__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, int n_parts, float* scr) {
+__device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, int n_parts, float* scr) {
     const int G = a.nh / a.nh_k;
     const int slots = a.n_parts;
     const int stride = a.d + 2;
@@ -79,42 +94,85 @@ __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, in
         const int gc = min(gc_max, G - g0);
         const int h0 = hk * G + g0;
         const float* base = a.parts + ((int64_t)(b * a.nh + h0) * slots) * stride;   // head g, part i at (g*slots + i)*stride
-        for (int idx = threadIdx.x; idx < gc * n_parts; idx += blockDim.x) {
-            const int64_t off = (int64_t)((idx / n_parts) * slots + idx % n_parts) * stride;
-            mm[idx] = __ldcg(base + off + a.d);
-            ll[idx] = __ldcg(base + off + a.d + 1);
+        // Staged path (the caller lent a big shared buffer and everything fits): every partial row is requested at once with
+        // 8-byte cp.async in one short rolled loop, so the merge costs ONE L2 round trip and very little code (this path runs
+        // on a different SM every launch: its instructions are cold, a long unrolled body costs more than the data).
+        const int row8 = stride / 2;                                              // 8-byte units per row (d + 2 is even)
+        const bool staged = a.big != nullptr && (stride & 1) == 0 && (int64_t)gc * n_parts * stride <= a.big_floats &&
+                            ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(slots * stride * 4)) & 7) == 0;
+        if (staged) {
+            const uint32_t big_s = (uint32_t)__cvta_generic_to_shared(a.big);
+            // a warp per row; no integer divisions anywhere on this path (it is the serial tail of the launch)
+            for (int g = 0; g < gc; ++g)
+                for (int i = threadIdx.x >> 5; i < n_parts; i += blockDim.x >> 5) {
+                    const float* src = base + (int64_t)(g * slots + i) * stride;
+                    const uint32_t dst = big_s + (uint32_t)((g * n_parts + i) * row8) * 8;
+                    for (int c = threadIdx.x & 31; c < row8; c += 32)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)c * 8), "l"(src + 2 * c) : "memory");
+                }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            dbg_stamp_m(a, 11);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            dbg_stamp_m(a, 12);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < gc * n_parts; idx += blockDim.x) {
+                mm[idx] = a.big[idx * stride + a.d];
+                ll[idx] = a.big[idx * stride + a.d + 1];
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < gc * n_parts; idx += blockDim.x) {
+                const int64_t off = (int64_t)((idx / n_parts) * slots + idx % n_parts) * stride;
+                mm[idx] = __ldcg(base + off + a.d);
+                ll[idx] = __ldcg(base + off + a.d + 1);
+            }
         }
         __syncthreads();
-        if (threadIdx.x < gc) {
-            const int g = threadIdx.x;
+        dbg_stamp_m(a, 9);
+        // weights: one warp per head, lanes over the parts
+        for (int g = threadIdx.x >> 5; g < gc; g += blockDim.x >> 5) {
+            const int lane = threadIdx.x & 31;
             float mstar = -INFINITY;
-            for (int i = 0; i < n_parts; ++i)
+            for (int i = lane; i < n_parts; i += 32)
                 if (ll[g * n_parts + i] > 0.f) mstar = fmaxf(mstar, mm[g * n_parts + i]);
+            mstar = warp_max(mstar);
             float den = 0.f;
-            for (int i = 0; i < n_parts; ++i) {
+            for (int i = lane; i < n_parts; i += 32) {
                 const float l = ll[g * n_parts + i];
                 const float w = (l > 0.f) ? exp2f(mm[g * n_parts + i] - mstar) : 0.f;
                 ww[g * n_parts + i] = w;
                 den += l * w;
             }
-            hd[2 * g] = mstar;
-            hd[2 * g + 1] = den;
+            den = warp_sum(den);
+            if (lane == 0) {
+                hd[2 * g] = mstar;
+                hd[2 * g + 1] = den;
+            }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < gc * a.d; idx += blockDim.x) {
-            const int g = idx / a.d, k = idx % a.d;
-            const float* src = base + (int64_t)g * slots * stride + k;
+        dbg_stamp_m(a, 10);
+        int g = 0, k = threadIdx.x;
+        while (k >= a.d) { k -= a.d; ++g; }
+        const int dg = blockDim.x / a.d, dk = blockDim.x - dg * a.d;     // one block stride in (head, dim) steps
+        for (; g < gc; g += dg, k += dk) {
+            if (k >= a.d) { k -= a.d; ++g; if (g >= gc) break; }
             const float* w = ww + g * n_parts;
             float acc = 0.f;
-            int i = 0;
-            for (; i + 8 <= n_parts; i += 8) {
-                float v[8];
+            if (staged) {
+                const float* src = a.big + (int64_t)g * n_parts * stride + k;
+#pragma unroll 4
+                for (int i = 0; i < n_parts; ++i) acc = fmaf(src[i * stride], w[i], acc);
+            } else {
+                const float* src = base + (int64_t)g * slots * stride + k;
+                int i = 0;
+                for (; i + 8 <= n_parts; i += 8) {
+                    float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(i + u) * stride);
+                    for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(i + u) * stride);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc = fmaf(v[u], w[i + u], acc);
+                    for (int u = 0; u < 8; ++u) acc = fmaf(v[u], w[i + u], acc);
+                }
+                for (; i < n_parts; ++i) acc = fmaf(__ldcg(src + (int64_t)i * stride), w[i], acc);
             }
-            for (; i < n_parts; ++i) acc = fmaf(__ldcg(src + (int64_t)i * stride), w[i], acc);
             const int h = h0 + g;
             if (a.partial_out) {
                 a.partial_out[(int64_t)(b * a.nh + h) * stride + k] = acc;
@@ -129,6 +187,15 @@ __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, in
         }
         __syncthreads();
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, int n_parts, float* scr, float* big = nullptr, int big_floats = 0, int dbg_piece = 0) {
+    MergeArgs m;
+    m.dbg_piece = dbg_piece;
+    m.big = big; m.big_floats = big_floats;
+    m.nh = a.nh; m.nh_k = a.nh_k; m.n_parts = a.n_parts; m.d = a.d; m.parts = a.parts; m.partial_out = a.partial_out; m.out = a.out; m.dbg_timing = a.dbg_timing;
+    merge_group_impl<T>(m, b, hk, n_parts, scr);
 }
 
 // Arrival ticket: returns true in every thread of the LAST CTA of group `grp` (of `expected` CTAs).

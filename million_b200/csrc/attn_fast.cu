@@ -52,7 +52,7 @@ int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, 
 // `np` parts of that group.
 template <typename T, int G, int VL>
 __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint32_t* __restrict__ prepared, const int gsub, const int split,
-                                                  const int hk, const int sub, const int b, const int t0, const int t1, const int np) {
+                                                  const int hk, const int sub, const int b, const int t0, const int t1, const int np, const int piece) {
     using namespace fast;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr uint32_t kLutOff = 0, kVtabOff = LutCfg<G>::bytes, kStageOff = kVtabOff + kVtabBytes;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             printf("million_b200: dynamic shared memory starts at 0x%x, expected 0x%x\n", smem_u32(smem), kSmemBase);
         __trap();
     }
-    dbg_stamp(a, 0);
+    dbg_stamp(a, 0, piece);
     const int Gfull = a.nh / a.nh_k;
     const int h0 = hk * Gfull + sub * G;                                // first query head of this CTA
     const int hb = b * a.nh_k + hk;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         }
     }
     __syncthreads();
-    dbg_stamp(a, 1);
+    dbg_stamp(a, 1, piece);
 
     // ---------------------------------------------------------------- main loop over this warp's tiles
     WarpState<G> st;
@@ -184,7 +184,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             for (int i = 0; i < 4; ++i) {
                 const int chunk = lane + i * 32;            // 0..127: 32 tokens * 4 chunks of 16 B
                 const int tok = tok0 + (chunk >> 2);
-                const int ok = (tile < n_tiles && tok < t1) ? 16 : 0;
+                const int ok = (tile < n_tiles && tok < t1 && !(a.dbg_mode & 4)) ? 16 : 0;
                 cp_async16(dst + chunk * 16, gbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
             }
             cp_async_commit();
@@ -243,6 +243,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             uint32_t words[16];
 #pragma unroll
             for (int w = 0; w < 16; ++w) words[w] = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));   // word (w + rot) % 16 of my row
+            if (!(a.dbg_mode & 1))
 #pragma unroll
             for (int w = 0; w < 16; ++w) {
 #pragma unroll
@@ -290,7 +291,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     if (nm[g] > st.m[g]) {
-                        const float alpha = exp2_safe(st.m[g], nm[g]);
+                        const float alpha = exp2_fast(st.m[g], nm[g]);
                         st.l[g] *= alpha;
 #pragma unroll
                         for (int sl = 0; sl < 4; ++sl) { st.o[sl][g][0] *= alpha; st.o[sl][g][1] *= alpha; }
@@ -301,7 +302,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             float p[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                p[g] = exp2_safe(s[g], st.m[g]);
+                p[g] = exp2_fast(s[g], st.m[g]);
                 st.l[g] += p[g];
             }
             // p for the PV phase: 4 halves (8 bytes) per token
@@ -313,6 +314,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             // ------------------------------------------------ PV: lane owns 4 sub-spaces (slot k -> 4*lq + ((k + hw) & 3))
             if constexpr (VL == 0) {
                 // row-major codes: a half-warp per token, the lane's word holds its 4 sub-spaces of that token
+                if (!(a.dbg_mode & 2))
 #pragma unroll 4
                 for (int jp = 0; jp < kTile / 2; ++jp) {
                     const int j = 2 * jp + hw;
@@ -386,6 +388,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         cp_async_wait<0>();
     }
 
+    dbg_stamp(a, 2, piece);
     // ---------------------------------------------------------------- my share of the fp16 window (exact attention)
     // The r recent tokens are dealt out to the splits of the group (r/S tokens each, one token per warp at a time), so no
     // CTA carries a long serial tail.  Lane owns dims 4*lane .. 4*lane+3.
@@ -402,28 +405,59 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 const float2 q01 = io<T>::to_f2(qr.x), q23 = io<T>::to_f2(qr.y);
                 qv[g][0] = q01.x * a.scale_log2; qv[g][1] = q01.y * a.scale_log2; qv[g][2] = q23.x * a.scale_log2; qv[g][3] = q23.y * a.scale_log2;
             }
-            for (int t = w0 + warp; t < w1; t += kWarps) {
-                const int64_t row = ((int64_t)hb * a.res_len + t) * 128 + 4 * lane;
-                const uint2 kr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
-                const uint2 vr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
-                const float2 k01 = io<T>::to_f2(kr.x), k23 = io<T>::to_f2(kr.y);
-                const float2 v01 = io<T>::to_f2(vr.x), v23 = io<T>::to_f2(vr.y);
+            // kWinBatch tokens per round: all their row loads are in flight together (a dependent load per token put ~1 us of loaded-memory
+            // latency on every one of them: 6.5 us per CTA at 32K, batch 8), then one softmax update per head for the whole round
+            constexpr int kWinBatch = 4;
+            for (int tb = w0 + warp; tb < w1; tb += kWinBatch * kWarps) {
+                uint2 kr[kWinBatch], vr[kWinBatch];
+#pragma unroll
+                for (int u = 0; u < kWinBatch; ++u) {
+                    const int t = tb + u * kWarps;
+                    const int64_t row = ((int64_t)hb * a.res_len + (t < w1 ? t : tb)) * 128 + 4 * lane;
+                    kr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
+                    vr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
+                }
+                float sg[kWinBatch][G];
+#pragma unroll
+                for (int u = 0; u < kWinBatch; ++u) {
+                    const float2 k01 = io<T>::to_f2(kr[u].x), k23 = io<T>::to_f2(kr[u].y);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) sg[u][g] = fmaf(qv[g][3], k23.y, fmaf(qv[g][2], k23.x, fmaf(qv[g][1], k01.y, qv[g][0] * k01.x)));
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                    for (int u = 0; u < kWinBatch; ++u)
+#pragma unroll
+                        for (int g = 0; g < G; ++g) sg[u][g] += __shfl_xor_sync(0xffffffffu, sg[u][g], off);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const float sg = warp_sum(fmaf(qv[g][3], k23.y, fmaf(qv[g][2], k23.x, fmaf(qv[g][1], k01.y, qv[g][0] * k01.x))));
-                    const float nm = fmaxf(wm[g], sg);
-                    const float alpha = exp2_safe(wm[g], nm), pw = exp2f(sg - nm);
-                    wl[g] = wl[g] * alpha + pw;
-                    wo[g][0] = fmaf(pw, v01.x, wo[g][0] * alpha); wo[g][1] = fmaf(pw, v01.y, wo[g][1] * alpha);
-                    wo[g][2] = fmaf(pw, v23.x, wo[g][2] * alpha); wo[g][3] = fmaf(pw, v23.y, wo[g][3] * alpha);
+                    float nm = wm[g];
+#pragma unroll
+                    for (int u = 0; u < kWinBatch; ++u) {
+                        if (tb + u * kWarps >= w1) sg[u][g] = -INFINITY;
+                        nm = fmaxf(nm, sg[u][g]);
+                    }
+                    const float alpha = exp2_fast(wm[g], nm);
+                    wl[g] *= alpha;
+                    wo[g][0] *= alpha; wo[g][1] *= alpha; wo[g][2] *= alpha; wo[g][3] *= alpha;
+#pragma unroll
+                    for (int u = 0; u < kWinBatch; ++u) {
+                        const float pw = exp2_fast(sg[u][g], nm);
+                        const float2 v01 = io<T>::to_f2(vr[u].x), v23 = io<T>::to_f2(vr[u].y);
+                        wl[g] += pw;
+                        wo[g][0] = fmaf(pw, v01.x, wo[g][0]); wo[g][1] = fmaf(pw, v01.y, wo[g][1]);
+                        wo[g][2] = fmaf(pw, v23.x, wo[g][2]); wo[g][3] = fmaf(pw, v23.y, wo[g][3]);
+                    }
                     wm[g] = nm;
                 }
             }
         }
     }
 
+    dbg_stamp(a, 7, piece);
     __syncthreads();   // every warp is done with its stage buffers and p slots (aliased below)
-    dbg_stamp(a, 2);
+    dbg_stamp(a, 3, piece);
     // ---------------------------------------------------------------- combine the warps of this CTA -> one partial state
     // 2 * kWarps entries of [G*128 o | G m | G l]: entry w = coded tokens of warp w, entry kWarps + w = its window tokens.
     // Coded layout: slot sl of lane (hw, lq) holds sub-space 4*lq + ((sl + hw) & 3); hw=1 is folded into hw=0 first.
@@ -481,13 +515,12 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             }
         }
     }
-    dbg_stamp(a, 3);
-    dbg_stamp(a, 4);
+    dbg_stamp(a, 4, piece);
     // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
     const bool last = last_cta_of_group(a.counters, hb, np * gsub, flag);
-    dbg_stamp(a, 5);
-    if (last) merge_group<T>(a, b, hk, np, xch);
-    dbg_stamp(a, 6);
+    dbg_stamp(a, 5, piece);
+    if (last) merge_group<T>(a, b, hk, np, xch, reinterpret_cast<float*>(lut_p), LutCfg<G>::bytes / 4, piece);   // the K LUT is dead by now
+    dbg_stamp(a, 6, piece);
 }
 
 // VL = 0: value codes row-major (tokens x 64 bytes); VL = 1: transposed per sub-space (paged pool or (M, ld) rows)
@@ -497,7 +530,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         // grid (splits, kv heads x 4-head sub-groups, batch): one segment per CTA
         int t0, t1;
         split_range(a, blockIdx.x, t0, t1);
-        attn_fast_segment<T, G, VL>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits);
+        attn_fast_segment<T, G, VL>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits, 0);
         return;
     }
     // Flat scheduling: the (group, 64-token unit) space is cut into runs of equal COST, one per CTA, so every SM gets the
@@ -510,6 +543,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
     const long long total = (long long)a.bs * a.nh_k * vg;
     const long long run0 = (long long)blockIdx.x * per;
     const long long run1 = (run0 + per < total) ? run0 + per : total;
+    int piece = 0;
     for (int grp = (int)(run0 / vg); grp < a.bs * a.nh_k && (long long)grp * vg < run1; ++grp) {
         const long long real0 = (long long)grp * vg + fast::kFlatPad, real1 = real0 + ug;   // this group's real units in the cut space
         const long long s0 = run0 > real0 ? run0 : real0, s1 = run1 < real1 ? run1 : real1;
@@ -517,7 +551,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         const int first = (int)(real0 / per), last = (int)((real1 - 1) / per);
         const int us = (int)(s0 - real0), ue = (int)(s1 - real0);
         const int t1 = (ue * 64 < a.nk) ? ue * 64 : a.nk;
-        attn_fast_segment<T, G, VL>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1);
+        attn_fast_segment<T, G, VL>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1, piece++);
         __syncthreads();   // the next piece reuses every shared buffer
     }
 }

@@ -61,6 +61,7 @@ static int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float*
 }
 
 static unsigned long long* g_dbg_timing = nullptr;
+static int g_dbg_mode = 0;
 static inline int elem_bytes(int dtype) { return dtype == MILLION_F32 ? 4 : 2; }
 
 }  // namespace million
@@ -213,6 +214,7 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     MILLION_REQUIRE(S + 1 <= 1024, "attn: at most 1023 splits");
     a.scale_log2 = kLog2e / sqrtf((float)p->d);
     a.dbg_timing = g_dbg_timing;
+    a.dbg_mode = g_dbg_mode;
 
     cudaStream_t st = (cudaStream_t)stream;
     if (p->impl == MILLION_IMPL_GENERIC) return launch_attn_generic(a, p->io_dtype, st);
@@ -223,6 +225,7 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
 }
 
 /* debug hook (not part of the public header): per-CTA phase time stamps of the decode-attention kernels */
+void million_debug_set_mode(int m) { g_dbg_mode = m; }
 void million_debug_set_timing_buffer(void* buf) { g_dbg_timing = reinterpret_cast<unsigned long long*>(buf); }
 
 int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, million_stream_t stream) {

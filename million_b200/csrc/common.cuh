@@ -92,6 +92,14 @@ __device__ __forceinline__ float exp2_safe(float x, float ref) {
     return (ref == -INFINITY) ? 0.f : exp2f(x - ref);
 }
 
+// same, one MUFU.EX2 (ex2.approx.ftz: 2 ulp, arguments below -126 flush to 0) instead of exp2f's range handling: for the
+// inner loops, where x - ref <= a few units by construction
+__device__ __forceinline__ float exp2_fast(float x, float ref) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x - ref));
+    return (ref == -INFINITY) ? 0.f : r;
+}
+
 // ---------------------------------------------------------------- streaming loads
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
     uint4 r;
