@@ -66,6 +66,9 @@ __device__ __forceinline__ int v_code_at(const AttnArgs& a, int hb, int j, int m
 // round trips per head and per part used to put 10 us on the tail of every batch-1 launch.
 // `scr` = shared scratch of kMergeScratch floats.
 constexpr int kMergeScratch = 3 * 2048 + 64;
+// floats per partial-state row [o (d) | m | l] in the kernels' workspace, padded to 16 bytes so that rows can be bulk-copied
+__host__ __device__ __forceinline__ constexpr int part_stride(int d) { return (d + 2 + 3) & ~3; }
+
 struct MergeArgs {
     int nh, nh_k, n_parts, d;
     const float* parts;
@@ -73,6 +76,7 @@ struct MergeArgs {
     void* out;
     float* big;            // optional large shared staging buffer lent by the caller (dead tables), big_floats floats
     int big_floats;
+    unsigned long long* bar;   // 8 bytes of shared memory for the mbarrier of the staged path
     unsigned long long* dbg_timing;
     int dbg_piece;
 };
@@ -83,7 +87,8 @@ template <typename T>
 __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, int n_parts, float* scr) {
     const int G = a.nh / a.nh_k;
     const int slots = a.n_parts;
-    const int stride = a.d + 2;
+    const int stride = part_stride(a.d);    // workspace rows
+    const int ostride = a.d + 2;            // rows of partial_out (public layout)
     float* mm = scr;               // [gc][n_parts] running max of each part
     float* ll = scr + 2048;        // [gc][n_parts] denominators
     float* ww = scr + 4096;        // [gc][n_parts] merge weights
@@ -94,27 +99,42 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
         const int gc = min(gc_max, G - g0);
         const int h0 = hk * G + g0;
         const float* base = a.parts + ((int64_t)(b * a.nh + h0) * slots) * stride;   // head g, part i at (g*slots + i)*stride
-        // Staged path (the caller lent a big shared buffer and everything fits): every partial row is requested at once with
-        // 8-byte cp.async in one short rolled loop, so the merge costs ONE L2 round trip and very little code (this path runs
-        // on a different SM every launch: its instructions are cold, a long unrolled body costs more than the data).
-        const int row8 = stride / 2;                                              // 8-byte units per row (d + 2 is even)
-        const bool staged = a.big != nullptr && (stride & 1) == 0 && (int64_t)gc * n_parts * stride <= a.big_floats &&
-                            ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(slots * stride * 4)) & 7) == 0;
+        // Staged path (the caller lent a big shared buffer and everything fits): one TMA bulk copy per head brings all its
+        // partial rows to shared memory, so the merge costs ONE L2 round trip and a handful of instructions.  It runs on a
+        // different SM every launch (its code is cold) and it is the serial tail of the launch: per-element copies
+        // (cp.async, ld.cg) spent 2-3 us here just being issued.
+        const bool staged = a.big != nullptr && a.bar != nullptr && (int64_t)gc * n_parts * stride <= a.big_floats;
         if (staged) {
-            const uint32_t big_s = (uint32_t)__cvta_generic_to_shared(a.big);
-            // a warp per row; no integer divisions anywhere on this path (it is the serial tail of the launch)
-            for (int g = 0; g < gc; ++g)
-                for (int i = threadIdx.x >> 5; i < n_parts; i += blockDim.x >> 5) {
-                    const float* src = base + (int64_t)(g * slots + i) * stride;
-                    const uint32_t dst = big_s + (uint32_t)((g * n_parts + i) * row8) * 8;
-                    for (int c = threadIdx.x & 31; c < row8; c += 32)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)c * 8), "l"(src + 2 * c) : "memory");
-                }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            const uint32_t big_s = (uint32_t)__cvta_generic_to_shared(a.big), bar_s = (uint32_t)__cvta_generic_to_shared(a.bar);
+            if (n_parts < 8) {
+                // few rows (large batches: 2-3 parts per group, merged in mid-kernel): 16-byte cp.async, a warp per row, is
+                // cheaper than setting up a bulk copy
+                for (int g = 0; g < gc; ++g)
+                    for (int i = threadIdx.x >> 5; i < n_parts; i += blockDim.x >> 5) {
+                        const float* src = base + (int64_t)(g * slots + i) * stride;
+                        const uint32_t dst = big_s + (uint32_t)((g * n_parts + i) * stride) * 4;
+                        for (int c = threadIdx.x & 31; c < stride / 4; c += 32)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)c * 16), "l"(src + 4 * c) : "memory");
+                    }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            } else if (threadIdx.x == 0) {
+                const uint32_t bytes = (uint32_t)(n_parts * stride * 4);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");   // barrier init + earlier generic accesses of `big` / other CTAs' rows
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * (uint32_t)gc) : "memory");
+                for (int g = 0; g < gc; ++g)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(big_s + (uint32_t)g * bytes),
+                                 "l"(base + (int64_t)g * slots * stride), "r"(bytes), "r"(bar_s)
+                                 : "memory");
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_s) : "memory");
+                asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar_s) : "memory");
+            }
             dbg_stamp_m(a, 11);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            dbg_stamp_m(a, 12);
             __syncthreads();
+            dbg_stamp_m(a, 12);
             for (int idx = threadIdx.x; idx < gc * n_parts; idx += blockDim.x) {
                 mm[idx] = a.big[idx * stride + a.d];
                 ll[idx] = a.big[idx * stride + a.d + 1];
@@ -159,7 +179,7 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
             float acc = 0.f;
             if (staged) {
                 const float* src = a.big + (int64_t)g * n_parts * stride + k;
-#pragma unroll 4
+#pragma unroll 6
                 for (int i = 0; i < n_parts; ++i) acc = fmaf(src[i * stride], w[i], acc);
             } else {
                 const float* src = base + (int64_t)g * slots * stride + k;
@@ -175,10 +195,10 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
             }
             const int h = h0 + g;
             if (a.partial_out) {
-                a.partial_out[(int64_t)(b * a.nh + h) * stride + k] = acc;
+                a.partial_out[(int64_t)(b * a.nh + h) * ostride + k] = acc;
                 if (k == 0) {
-                    a.partial_out[(int64_t)(b * a.nh + h) * stride + a.d] = hd[2 * g] * kLn2;   // natural-log units
-                    a.partial_out[(int64_t)(b * a.nh + h) * stride + a.d + 1] = hd[2 * g + 1];
+                    a.partial_out[(int64_t)(b * a.nh + h) * ostride + a.d] = hd[2 * g] * kLn2;   // natural-log units
+                    a.partial_out[(int64_t)(b * a.nh + h) * ostride + a.d + 1] = hd[2 * g + 1];
                 }
             } else {
                 const float den = hd[2 * g + 1];
@@ -190,8 +210,9 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
 }
 
 template <typename T>
-__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, int n_parts, float* scr, float* big = nullptr, int big_floats = 0, int dbg_piece = 0) {
+__device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, int n_parts, float* scr, float* big = nullptr, int big_floats = 0, unsigned long long* bar = nullptr, int dbg_piece = 0) {
     MergeArgs m;
+    m.bar = bar;
     m.dbg_piece = dbg_piece;
     m.big = big; m.big_floats = big_floats;
     m.nh = a.nh; m.nh_k = a.nh_k; m.n_parts = a.n_parts; m.d = a.d; m.parts = a.parts; m.partial_out = a.partial_out; m.out = a.out; m.dbg_timing = a.dbg_timing;

@@ -509,7 +509,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                     o = fmaf(ex[g * 128 + dim], sc, o);
                     l = fmaf(ex[G * 128 + G + g], sc, l);
                 }
-                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * a.n_parts + split) * 130;
+                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * a.n_parts + split) * part_stride(128);
                 part[dim] = o;
                 if (dim == 0) { part[128] = mstar; part[129] = l; }
             }
@@ -519,7 +519,8 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
     // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
     const bool last = last_cta_of_group(a.counters, hb, np * gsub, flag);
     dbg_stamp(a, 5, piece);
-    if (last) merge_group<T>(a, b, hk, np, xch, reinterpret_cast<float*>(lut_p), LutCfg<G>::bytes / 4, piece);   // the K LUT is dead by now
+    if (last) merge_group<T>(a, b, hk, np, xch, reinterpret_cast<float*>(lut_p), LutCfg<G>::bytes / 4,
+                             reinterpret_cast<unsigned long long*>(smem + kMiscOff + 160), piece);   // the K LUT is dead by now
     dbg_stamp(a, 6, piece);
 }
 

@@ -379,7 +379,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                     o = fmaf(ex[g * 128 + dim], sc, o);
                     l = fmaf(ex[G * 128 + G + g], sc, l);
                 }
-                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * a.n_parts + split) * 130;
+                float* part = a.parts + ((int64_t)(b * a.nh + h0 + g) * a.n_parts + split) * part_stride(128);
                 part[dim] = o;
                 if (dim == 0) { part[128] = mstar; part[129] = l; }
             }

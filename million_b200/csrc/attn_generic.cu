@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
             }
             __syncthreads();
         }
-        float* part = a.parts + ((int64_t)(b * a.nh + h) * n_parts + split) * (a.d + 2);
+        float* part = a.parts + ((int64_t)(b * a.nh + h) * n_parts + split) * part_stride(a.d);
 #pragma unroll
         for (int u = 0; u < 2; ++u)
             if (tid + u * 128 < a.d) part[tid + u * 128] = acc[u];

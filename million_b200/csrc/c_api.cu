@@ -166,7 +166,7 @@ int million_pq_decode_attn_default_splits(int bs, int nh_k, int nk) {
 
 int64_t million_pq_decode_attn_workspace_bytes(int bs, int nh, int nh_k, int d, int max_splits) {
     const int64_t counters = ((int64_t)bs * nh_k * 4 + 255) / 256 * 256;
-    return counters + (int64_t)bs * nh * (max_splits + 2) * (d + 2) * 4;   // +2: window part (generic) / boundary pieces (flat)
+    return counters + (int64_t)bs * nh * (max_splits + 2) * part_stride(d) * 4;   // +2: window part (generic) / boundary pieces (flat)
 }
 
 int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream) {
@@ -207,7 +207,7 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     a.res_len = p->res_len; a.v_layout = p->v_layout; a.page_size = p->page_size; a.n_pages = p->n_pages;
     a.n_splits = S;
     a.auto_splits = p->n_splits <= 0;
-    a.ws_parts = (int)((p->workspace_bytes - (((int64_t)p->bs * p->nh_k * 4 + 255) / 256 * 256)) / ((int64_t)p->bs * p->nh * (p->d + 2) * 4));
+    a.ws_parts = (int)((p->workspace_bytes - (((int64_t)p->bs * p->nh_k * 4 + 255) / 256 * 256)) / ((int64_t)p->bs * p->nh * part_stride(p->d) * 4));
     const int units = (p->nk + 15) / 16;
     a.units_per_split = ((units + S - 1) / S + 3) / 4 * 4;   // splits start on multiples of 64 tokens (tiles never straddle a page)
     if (a.units_per_split < 4) a.units_per_split = 4;
