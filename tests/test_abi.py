@@ -53,7 +53,7 @@ def test_struct_layout_matches_header(lib, tmp_path):
 def test_abi_version_and_pure_functions(lib):
     h = lib.lib()
     assert h.million_abi_version() == lib.ABI_VERSION
-    assert h.million_pq_decode_attn_workspace_bytes(1, 32, 8, 128, 18) == 256 + 32 * 20 * 130 * 4
+    assert h.million_pq_decode_attn_workspace_bytes(1, 32, 8, 128, 18) == 256 + 32 * 20 * 132 * 4   # rows of d + 2 floats padded to 16 bytes
 
 
 def test_argument_errors_are_status_codes(lib):
