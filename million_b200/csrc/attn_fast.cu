@@ -306,7 +306,9 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 st.l[g] += p[g];
             }
             // p for the PV phase: 4 halves (8 bytes) per token
-            *reinterpret_cast<uint2*>(pbuf_w + lane * 8) = make_uint2(as_u32(__floats2half2_rn(p[0], p[1])), as_u32(__floats2half2_rn(p[2], p[3])));
+            // row-major V: slot = token with its two low bits swapped (tokens t and t+2 adjacent); transposed V: natural order
+            const int p_slot = VL == 0 ? ((lane & ~3) | ((lane & 1) << 1) | ((lane >> 1) & 1)) : lane;
+            *reinterpret_cast<uint2*>(pbuf_w + p_slot * 8) = make_uint2(as_u32(__floats2half2_rn(p[0], p[1])), as_u32(__floats2half2_rn(p[2], p[3])));
 
             cp_async_wait<1>();          // pending [V(i), K(i+1)] -> V(i) landed
             __syncwarp();
@@ -314,22 +316,29 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             // ------------------------------------------------ PV: lane owns 4 sub-spaces (slot k -> 4*lq + ((k + hw) & 3))
             if constexpr (VL == 0) {
                 // row-major codes: a half-warp per token, the lane's word holds its 4 sub-spaces of that token
+                // The half-warp takes tokens 4*jq + hw and 4*jq + hw + 2 of every group of four (their rows lie 16 banks away
+                // from the other half-warp's: conflict free); the p slots of those two tokens are adjacent (see p_slot), so ONE
+                // 16-byte broadcast load brings both.
                 if (!(a.dbg_mode & 2))
-#pragma unroll 4
-                for (int jp = 0; jp < kTile / 2; ++jp) {
-                    const int j = 2 * jp + hw;
-                    const uint32_t word = lds32(vsp, j * kRowBytes + lq * 4);
-                    const uint2 pk = lds64(pbuf_w, j * 8);
-                    const __half2 p01 = as_h2(pk.x), p23 = as_h2(pk.y);
+#pragma unroll 2
+                for (int jq = 0; jq < kTile / 4; ++jq) {
+                    const uint4 pk = lds128(pbuf_w, (4 * jq + 2 * hw) * 8);
+                    uint32_t word[2];
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) {
-                        const uint32_t ad = __byte_perm(word, sl < 2 ? voff01 : voff23, vsel[sl]);
-                        const __half2 v = as_h2(gather32<kSmemBase + kVtabOff>(ad));
-                        acc[sl][0] = __hfma2(__low2half2(p01), v, acc[sl][0]);
-                        if constexpr (G >= 2) acc[sl][1] = __hfma2(__high2half2(p01), v, acc[sl][1]);
-                        if constexpr (G == 4) {
-                            acc[sl][2] = __hfma2(__low2half2(p23), v, acc[sl][2]);
-                            acc[sl][3] = __hfma2(__high2half2(p23), v, acc[sl][3]);
+                    for (int u = 0; u < 2; ++u) word[u] = lds32(vsp, (4 * jq + hw + 2 * u) * kRowBytes + lq * 4);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const __half2 p01 = as_h2(u ? pk.z : pk.x), p23 = as_h2(u ? pk.w : pk.y);
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl) {
+                            const uint32_t ad = __byte_perm(word[u], sl < 2 ? voff01 : voff23, vsel[sl]);
+                            const __half2 v = as_h2(gather32<kSmemBase + kVtabOff>(ad));
+                            acc[sl][0] = __hfma2(__low2half2(p01), v, acc[sl][0]);
+                            if constexpr (G >= 2) acc[sl][1] = __hfma2(__high2half2(p01), v, acc[sl][1]);
+                            if constexpr (G == 4) {
+                                acc[sl][2] = __hfma2(__low2half2(p23), v, acc[sl][2]);
+                                acc[sl][3] = __hfma2(__high2half2(p23), v, acc[sl][3]);
+                            }
                         }
                     }
                 }
