@@ -21,6 +21,10 @@
 
 namespace million {
 
+#ifndef MILLION_QK_PARTS
+#define MILLION_QK_PARTS 1
+#endif
+constexpr int kQkParts = MILLION_QK_PARTS;   // 1 = the 64 QK gathers of a tile fully unrolled
 
 // ------------------------------------------------------------------------------------------------
 // Codebook preparation (once per codebook): fp16 tables in the column order the kernel gathers with.
@@ -77,27 +81,100 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
     const int hb = b * a.nh_k + hk;
     const bool has_codes = t1 > t0;
 
+    // ---------------------------------------------------------------- per-lane constants and tile streaming (used from the prologue on)
+    const int lq = lane & 15, hw = lane >> 4;
+    const int rot = (lq + hw) & 15;
+    unsigned char* ksp = stage_p + warp * kStageBytes;
+    unsigned char* vsp = ksp + kTile * kRowBytes;
+    unsigned char* pbuf_w = pbuf_p + warp * kTile * 8;
+    const uint32_t ks_s = smem_u32(ksp), vs_s = smem_u32(vsp);
+    const uint8_t* kbase = a.k_codes + hb * a.k_head_stride;
+    const uint8_t* vbase = a.v_codes + (a.v_layout == MILLION_V_PAGED ? 0 : hb * a.v_head_stride);
+
+    // per-lane gather constants
+    uint32_t koff[16];   // QK: byte0 = column offset for even b, byte1 = for odd b, bytes 2,3 = 0
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        const int Wl = (w + rot) & 15;
+        if constexpr (G == 4) koff[w] = (uint32_t)(Wl * 8) | ((uint32_t)(Wl * 8 + 128) << 8);
+        else koff[w] = (uint32_t)(Wl * 4) | ((uint32_t)(Wl * 4 + 64) << 8);   // + (bb>>1)*128 comes from the immediate
+    }
+    // PV: slot s -> byte bb = (s + hw) & 3 of the lane's V code word; column offset col_of(4*lq + bb) * 4
+    uint32_t voff01, voff23, vsel[4];
+    {
+        uint32_t o[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int bb = (s + hw) & 3;
+            o[s] = (uint32_t)(col_of(4 * lq + bb) * 4);
+            // result = [off (from voff, byte 4 + (s&1)), code (byte bb of the word), 0, 0]
+            vsel[s] = (uint32_t)(4 + (s & 1)) | ((uint32_t)bb << 4) | (6u << 8) | (6u << 12);
+        }
+        voff01 = o[0] | (o[1] << 8);
+        voff23 = o[2] | (o[3] << 8);
+    }
+
+    const int n_tiles = (t1 - t0 + kTile - 1) / kTile;
+    // one K buffer and one V buffer per warp; K(i+1) is requested right after QK(i), V(i+1) right after PV(i)
+    auto issue = [&](int tile, const uint8_t* gbase, uint32_t dst) {
+        const int tok0 = t0 + tile * kTile;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int chunk = lane + i * 32;            // 0..127: 32 tokens * 4 chunks of 16 B
+            const int tok = tok0 + (chunk >> 2);
+            const int ok = (tile < n_tiles && tok < t1 && !(a.dbg_mode & 4)) ? 16 : 0;
+            cp_async16(dst + chunk * 16, gbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
+        }
+        cp_async_commit();
+    };
+    // transposed value codes: the tile is 64 sub-space rows of 32 tokens; row m is staged at row pi(m) = m/4 + 16*(m%4)
+    // (32 bytes each) so that the word reads of the PV phase below are bank-conflict free
+    auto issue_vt = [&](int tile) {
+        const int tok0 = t0 + tile * kTile;
+        const bool in_range = tile < n_tiles;
+        const uint8_t* src0 = vbase;
+        int64_t row_stride = a.v_ld;
+        if (in_range) {
+            if (a.v_layout == MILLION_V_PAGED) {
+                const int64_t page = __ldg(a.v_page_ids + (int64_t)hb * a.n_pages + tok0 / a.page_size);
+                src0 = a.v_codes + page * 64 * a.page_size + (tok0 % a.page_size);
+                row_stride = a.page_size;
+            } else {
+                src0 = vbase + tok0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int chunk = lane + i * 32;            // 0..127: 64 rows * 2 chunks of 16 tokens
+            const int m = chunk >> 1, hc = chunk & 1;
+            int ok = in_range ? (t1 - (tok0 + hc * 16)) : 0;
+            ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
+            const uint32_t dst = vs_s + (uint32_t)((((m >> 2) + 16 * (m & 3)) * 32) + hc * 16);
+            cp_async16(dst, (ok ? src0 : vbase) + (ok ? (int64_t)m * row_stride + hc * 16 : 0), ok);
+        }
+        cp_async_commit();
+    };
+    auto issue_v = [&](int tile) {
+        if constexpr (VL == 0) issue(tile, vbase, vs_s);
+        else issue_vt(tile);
+    };
+
     // ---------------------------------------------------------------- prologue: V table + K LUT
     if (has_codes) {
-        // The K gather table kT (64 KB, L2 resident) streams through the stage area in four 16 KB chunks (cp.async double
-        // buffer); the V table (already in gather order) is copied straight to its place in the background.
-        const uint32_t stage0 = smem_u32(stage_p), vtab_s = smem_u32(smem + kVtabOff);
-        auto load_chunk = [&](int ch) {
-            const char* src = reinterpret_cast<const char*>(prepared) + ch * 16384;
-            const uint32_t dst = stage0 + (ch & 1) * 16384;
-#pragma unroll
-            for (int i = 0; i < 16384 / 16 / kThreads; ++i) cp_async16(dst + (tid + i * kThreads) * 16, src + (tid + i * kThreads) * 16, 16);
-            cp_async_commit();
-        };
-        load_chunk(0);
+        // The V table (already in gather order) is copied to its place in the background, and this warp's first K and V tiles
+        // are requested right away: their HBM latency hides behind the LUT build (the stage area is not used for anything else).
         {
+            const uint32_t vtab_s = smem_u32(smem + kVtabOff);
             const uint4* vsrc = reinterpret_cast<const uint4*>(prepared + 64 * 256);
             for (int i = tid; i < kVtabBytes / 16; i += kThreads) cp_async16(vtab_s + i * 16, vsrc + i, 16);
             cp_async_commit();
         }
-        load_chunk(1);
+        issue(warp, kbase, ks_s);
+        issue_v(warp);
         // K LUT: thread owns column `col` (= one sub-space) and walks the codes.  LUT[c][col] = <q_h[m], Kcent[m][c]> for the
-        // G heads of the group: fp32 products of fp16 operands, rounded once to fp16 (G=1 keeps fp32 entries).
+        // G heads of the group: fp32 products of fp16 operands, rounded once to fp16 (G=1 keeps fp32 entries).  The gather table
+        // kT (64 KB, L2 resident) is read straight into registers, 16 coalesced loads in flight per thread (staging it through
+        // shared memory cost four block barriers and kept the stage area busy).
         const int col = tid & 63;
         const int bb = ((col >> 5) << 1) | ((col >> 4) & 1), W = col & 15, m = 4 * W + bb;
         float q0[G], q1[G];
@@ -107,34 +184,33 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             q0[g] = io<T>::to_f(q[2 * m]);
             q1[g] = io<T>::to_f(q[2 * m + 1]);
         }
-        for (int ch = 0; ch < 4; ++ch) {
-            if (ch == 0) cp_async_wait<2>();        // pending: [chunk0, vtab, chunk1] -> chunk0 landed
-            else if (ch < 3) cp_async_wait<1>();    // chunk ch landed (and the V table)
-            else cp_async_wait<0>();
-            __syncthreads();
-            const unsigned char* src = stage_p + (ch & 1) * 16384;
-            // fp32 products of exact fp16 operands, rounded once to fp16 (a packed-half build is 0.7 us faster per CTA but
-            // costs a second rounding, visible on peaked score distributions)
-#pragma unroll 4
-            for (int cl = tid >> 6; cl < 64; cl += kThreads / 64) {
-                const int c = ch * 64 + cl;
-                const __half2 cv = as_h2(*reinterpret_cast<const uint32_t*>(src + (cl * 64 + col) * 4));
-                const float c0 = __low2float(cv), c1 = __high2float(cv);
+        constexpr int kRowsPerPass = kThreads / 64, kBatch = 16;
+#pragma unroll 1
+        for (int c0 = tid >> 6; c0 < 256; c0 += kRowsPerPass * kBatch) {
+            uint32_t raw[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) raw[u] = __ldg(prepared + (c0 + u * kRowsPerPass) * 64 + col);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int c = c0 + u * kRowsPerPass;
+                const __half2 cv = as_h2(raw[u]);
+                const float c0f = __low2float(cv), c1f = __high2float(cv);
+                // fp32 products of exact fp16 operands, rounded once to fp16 (a packed-half build is 0.7 us faster per CTA but
+                // costs a second rounding, visible on peaked score distributions)
                 if constexpr (G == 4) {
-                    const __half2 e01 = __floats2half2_rn(fmaf(c1, q1[0], c0 * q0[0]), fmaf(c1, q1[1], c0 * q0[1]));
-                    const __half2 e23 = __floats2half2_rn(fmaf(c1, q1[2], c0 * q0[2]), fmaf(c1, q1[3], c0 * q0[3]));
+                    const __half2 e01 = __floats2half2_rn(fmaf(c1f, q1[0], c0f * q0[0]), fmaf(c1f, q1[1], c0f * q0[1]));
+                    const __half2 e23 = __floats2half2_rn(fmaf(c1f, q1[2], c0f * q0[2]), fmaf(c1f, q1[3], c0f * q0[3]));
                     // address(m, c) = (b>>1)*64K + c*256 + ((b&1)*16 + W)*8
                     *reinterpret_cast<uint2*>(lut_p + (bb >> 1) * 65536 + c * 256 + ((bb & 1) * 16 + W) * 8) = make_uint2(as_u32(e01), as_u32(e23));
                 } else if constexpr (G == 2) {
-                    const __half2 e01 = __floats2half2_rn(fmaf(c1, q1[0], c0 * q0[0]), fmaf(c1, q1[1], c0 * q0[1]));
+                    const __half2 e01 = __floats2half2_rn(fmaf(c1f, q1[0], c0f * q0[0]), fmaf(c1f, q1[1], c0f * q0[1]));
                     *reinterpret_cast<uint32_t*>(lut_p + c * 256 + col * 4) = as_u32(e01);
                 } else {
-                    *reinterpret_cast<float*>(lut_p + c * 256 + col * 4) = fmaf(c1, q1[0], c0 * q0[0]);
+                    *reinterpret_cast<float*>(lut_p + c * 256 + col * 4) = fmaf(c1f, q1[0], c0f * q0[0]);
                 }
             }
-            __syncthreads();
-            if (ch + 2 < 4) load_chunk(ch + 2);
         }
+        cp_async_wait<2>();    // pending: [V table, K(0), V(0)] -> my part of the V table has landed
     }
     __syncthreads();
     dbg_stamp(a, 1, piece);
@@ -144,85 +220,6 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
     state_init(st);
 
     if (has_codes) {
-        const int lq = lane & 15, hw = lane >> 4;
-        const int rot = (lq + hw) & 15;
-        unsigned char* ksp = stage_p + warp * kStageBytes;
-        unsigned char* vsp = ksp + kTile * kRowBytes;
-        unsigned char* pbuf_w = pbuf_p + warp * kTile * 8;
-        const uint32_t ks_s = smem_u32(ksp), vs_s = smem_u32(vsp);
-        const uint8_t* kbase = a.k_codes + hb * a.k_head_stride;
-        const uint8_t* vbase = a.v_codes + (a.v_layout == MILLION_V_PAGED ? 0 : hb * a.v_head_stride);
-
-        // per-lane gather constants
-        uint32_t koff[16];   // QK: byte0 = column offset for even b, byte1 = for odd b, bytes 2,3 = 0
-#pragma unroll
-        for (int w = 0; w < 16; ++w) {
-            const int Wl = (w + rot) & 15;
-            if constexpr (G == 4) koff[w] = (uint32_t)(Wl * 8) | ((uint32_t)(Wl * 8 + 128) << 8);
-            else koff[w] = (uint32_t)(Wl * 4) | ((uint32_t)(Wl * 4 + 64) << 8);   // + (bb>>1)*128 comes from the immediate
-        }
-        // PV: slot s -> byte bb = (s + hw) & 3 of the lane's V code word; column offset col_of(4*lq + bb) * 4
-        uint32_t voff01, voff23, vsel[4];
-        {
-            uint32_t o[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int bb = (s + hw) & 3;
-                o[s] = (uint32_t)(col_of(4 * lq + bb) * 4);
-                // result = [off (from voff, byte 4 + (s&1)), code (byte bb of the word), 0, 0]
-                vsel[s] = (uint32_t)(4 + (s & 1)) | ((uint32_t)bb << 4) | (6u << 8) | (6u << 12);
-            }
-            voff01 = o[0] | (o[1] << 8);
-            voff23 = o[2] | (o[3] << 8);
-        }
-
-        const int n_tiles = (t1 - t0 + kTile - 1) / kTile;
-        // one K buffer and one V buffer per warp; K(i+1) is requested right after QK(i), V(i+1) right after PV(i)
-        auto issue = [&](int tile, const uint8_t* gbase, uint32_t dst) {
-            const int tok0 = t0 + tile * kTile;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int chunk = lane + i * 32;            // 0..127: 32 tokens * 4 chunks of 16 B
-                const int tok = tok0 + (chunk >> 2);
-                const int ok = (tile < n_tiles && tok < t1 && !(a.dbg_mode & 4)) ? 16 : 0;
-                cp_async16(dst + chunk * 16, gbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
-            }
-            cp_async_commit();
-        };
-        // transposed value codes: the tile is 64 sub-space rows of 32 tokens; row m is staged at row pi(m) = m/4 + 16*(m%4)
-        // (32 bytes each) so that the word reads of the PV phase below are bank-conflict free
-        auto issue_vt = [&](int tile) {
-            const int tok0 = t0 + tile * kTile;
-            const bool in_range = tile < n_tiles;
-            const uint8_t* src0 = vbase;
-            int64_t row_stride = a.v_ld;
-            if (in_range) {
-                if (a.v_layout == MILLION_V_PAGED) {
-                    const int64_t page = __ldg(a.v_page_ids + (int64_t)hb * a.n_pages + tok0 / a.page_size);
-                    src0 = a.v_codes + page * 64 * a.page_size + (tok0 % a.page_size);
-                    row_stride = a.page_size;
-                } else {
-                    src0 = vbase + tok0;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int chunk = lane + i * 32;            // 0..127: 64 rows * 2 chunks of 16 tokens
-                const int m = chunk >> 1, hc = chunk & 1;
-                int ok = in_range ? (t1 - (tok0 + hc * 16)) : 0;
-                ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
-                const uint32_t dst = vs_s + (uint32_t)((((m >> 2) + 16 * (m & 3)) * 32) + hc * 16);
-                cp_async16(dst, (ok ? src0 : vbase) + (ok ? (int64_t)m * row_stride + hc * 16 : 0), ok);
-            }
-            cp_async_commit();
-        };
-        auto issue_v = [&](int tile) {
-            if constexpr (VL == 0) issue(tile, vbase, vs_s);
-            else issue_vt(tile);
-        };
-        issue(warp, kbase, ks_s);
-        issue_v(warp);
-
         __half2 acc[4][G];
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl)
@@ -240,17 +237,12 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             float s[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) s[g] = 0.f;
-            uint32_t words[16];
-#pragma unroll
-            for (int w = 0; w < 16; ++w) words[w] = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));   // word (w + rot) % 16 of my row
-            if (!(a.dbg_mode & 1))
-#pragma unroll
-            for (int w = 0; w < 16; ++w) {
+            auto qk_gathers = [&](const uint32_t word, const uint32_t kf) {
 #pragma unroll
                 for (int bq = 0; bq < 4; ++bq) {
                     if constexpr (G == 4) {
                         constexpr uint32_t selc[4] = {0x6604u, 0x6615u, 0x6624u, 0x6635u};
-                        const uint32_t ad = __byte_perm(words[w], koff[w], selc[bq]);     // (code << 8) | column offset
+                        const uint32_t ad = __byte_perm(word, kf, selc[bq]);     // (code << 8) | column offset
                         const uint2 e = (bq >> 1) ? gather64<kSmemBase + kLutOff + 65536>(ad) : gather64<kSmemBase + kLutOff>(ad);
                         fhadd2(s[0], s[1], e.x);
                         fhadd2(s[2], s[3], e.y);
@@ -258,11 +250,35 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                         // the two half-warps use different bytes in the same step so that all 32 lanes hit 32 banks
                         constexpr uint32_t selc[4] = {0x6604u, 0x6615u, 0x6624u, 0x6635u};
                         const int b1 = (bq + 1) & 3;
-                        const uint32_t ad = __byte_perm(words[w], koff[w], hw ? selc[b1] : selc[bq]) + (uint32_t)(((hw ? b1 : bq) >> 1) * 128);
+                        const uint32_t ad = __byte_perm(word, kf, hw ? selc[b1] : selc[bq]) + (uint32_t)(((hw ? b1 : bq) >> 1) * 128);
                         const uint32_t e = gather32<kSmemBase + kLutOff>(ad);
                         if constexpr (G == 2) fhadd2(s[0], s[1], e);
                         else s[0] += __uint_as_float(e);
                     }
+                }
+            };
+            if constexpr (kQkParts == 1) {
+                uint32_t words[16];
+#pragma unroll
+                for (int w = 0; w < 16; ++w) words[w] = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));   // word (w + rot) % 16 of my row
+                if (!(a.dbg_mode & 1))
+#pragma unroll
+                    for (int w = 0; w < 16; ++w) qk_gathers(words[w], koff[w]);
+            } else {
+                // rolled in kQkParts passes (smaller loop body; the per-word constants are recomputed)
+                constexpr int kPer = 16 / kQkParts;
+#pragma unroll 1
+                for (int part = 0; part < kQkParts; ++part) {
+                    uint32_t words[kPer], kf[kPer];
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) {
+                        const uint32_t Wl = (uint32_t)(part * kPer + i + rot) & 15u;
+                        words[i] = lds32(ksp, lane * kRowBytes + (Wl << 2));
+                        kf[i] = G == 4 ? (Wl * 0x0808u + 0x8000u) : (Wl * 0x0404u + 0x4000u);
+                    }
+                    if (!(a.dbg_mode & 1))
+#pragma unroll
+                        for (int i = 0; i < kPer; ++i) qk_gathers(words[i], kf[i]);
                 }
             }
             __syncwarp();                                   // every lane has read its K row
@@ -572,7 +588,6 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
     using namespace fast;
     const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + 256;
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= 2 * kWarps * 4 * 130 * sizeof(float), "stage + p area too small for the combine");
-    static_assert(kWarps * kStageBytes >= 2 * 16384, "stage area too small for the LUT-build chunks");
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static bool configured = false;
     if (!configured) {
