@@ -159,14 +159,6 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         else issue_vt(tile);
     };
 
-    // my share of the fp16 window (see below) is needed only after the main loop: ask L2 for it now, so that the window phase
-    // pays an L2 hit instead of an HBM round trip per batch of rows
-    const int w0 = (int)((long long)a.r * split / np), w1 = (int)((long long)a.r * (split + 1) / np);
-    for (int i = tid; i < (w1 - w0) * 4; i += kThreads) {
-        const T* row = reinterpret_cast<const T*>((i & 2) ? a.v_res : a.k_res) + ((int64_t)hb * a.res_len + w0 + (i >> 2)) * 128 + (i & 1) * 64;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-    }
-
     // ---------------------------------------------------------------- prologue: V table + K LUT
     if (has_codes) {
         // The V table (already in gather order) is copied to its place in the background, and this warp's first K and V tiles
@@ -429,6 +421,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
 #pragma unroll
     for (int g = 0; g < G; ++g) { wm[g] = -INFINITY; wl[g] = 0.f; wo[g][0] = wo[g][1] = wo[g][2] = wo[g][3] = 0.f; }
     {
+        const int w0 = (int)((long long)a.r * split / np), w1 = (int)((long long)a.r * (split + 1) / np);
         if (w0 + warp < w1) {
             float qv[G][4];
 #pragma unroll
