@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MILLION_ABI_VERSION 4
+#define MILLION_ABI_VERSION 5
 
 typedef void* million_stream_t; /* cudaStream_t */
 
@@ -110,6 +110,24 @@ int million_pq_encode_paged(const void* x, int x_dtype, int64_t x_head_stride,
                             int n_heads, int n_tokens, int d, int M, int C,
                             int impl, million_stream_t stream);
 
+/* Outlier split (extension; no reference counterpart).  Per head-vector: the k_out entries of
+ * largest |x| (ties: lowest dim, listed largest first) are zeroed in x_masked — which the caller then encodes with
+ * million_pq_encode[_paged] — and recorded as (dim, delta) with delta = x[dim] - cent[m, code[m], k] rounded to x_dtype,
+ * code[m] being the arg-min of the MASKED sub-vector (same arithmetic as the encoder, so it equals the stored code).
+ *   x_masked   (n_heads, n_tokens, d) x_dtype, contiguous
+ *   out_idx    record (head, t0 + t, i) at out_idx + head*out_head_stride + (t0 + t)*k_out + i   (uint8; d <= 256)
+ *   out_val    same addressing, x_dtype */
+int million_pq_outlier_split(const void* x, int x_dtype, int64_t x_head_stride, const float* cent,
+                             void* x_masked, uint8_t* out_idx, void* out_val, int64_t out_head_stride, int64_t t0,
+                             int n_heads, int n_tokens, int d, int M, int C, int k_out, million_stream_t stream);
+
+/* out[head, t, idx[head, t0 + t, i]] += val[head, t0 + t, i]: the reconstruction with the side store applied
+ * (after million_pq_decode).  out (n_heads, n_tokens, d) with head stride in ELEMENTS, dtype f16/bf16/f32 (val: f16/bf16
+ * as val_dtype). */
+int million_pq_outlier_apply(void* out, int dtype, int64_t out_head_stride, const uint8_t* idx, const void* val, int val_dtype,
+                             int64_t store_head_stride, int64_t t0, int n_heads, int n_tokens, int d, int k_out,
+                             million_stream_t stream);
+
 /* Reconstruct: out[v, m*d_m + k] = cent[m, codes[v, m], k].  Replaces sa_decode_4d (pq_utils.py:501-540).
  * cent/out share `dtype` (the reference returns C's dtype).  codes addressed like in million_pq_encode. */
 int million_pq_decode(const void* codes, int code_bytes,
@@ -171,7 +189,21 @@ typedef struct million_attn_params {
     /* fp16 gather tables made by million_pq_codebook_prepare() from (k_cent, v_cent); required by the FAST
      * implementation (AUTO falls back to GENERIC when NULL).  Must be re-made whenever the codebooks change. */
     const void* prepared_codebook;
+
+    /* Outlier side store (extension; the reference has no outlier code).  Per coded
+     * token and KV head, k_out (K) / v_out (V) records (dim:uint8, delta:io_dtype): the reconstruction the attention runs
+     * on is decode(code) with x_hat[dim] += delta.  Layout (bs, nh_k, >= nk, k_out), head stride in RECORDS.
+     * k_out = v_out = 0 (or NULL pointers) = disabled: the path is bit-identical to the one without the store. */
+    int32_t k_out, v_out;
+    const uint8_t* k_out_idx;
+    const void* k_out_val;
+    int64_t k_out_head_stride;
+    const uint8_t* v_out_idx;
+    const void* v_out_val;
+    int64_t v_out_head_stride;
 } million_attn_params;
+
+#define MILLION_MAX_OUTLIERS 8
 
 #define MILLION_ATTN_PARTIAL_ONLY 1
 

@@ -14,7 +14,7 @@ MILLION_OK, MILLION_ERR_INVALID, MILLION_ERR_UNSUPPORTED, MILLION_ERR_CUDA = 0, 
 V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_FAST = 0, 1, 2
 ATTN_PARTIAL_ONLY = 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
 
@@ -37,6 +37,9 @@ class AttnParams(ctypes.Structure):
         ("k_cent", c_vp), ("v_cent", c_vp), ("k_res", c_vp), ("v_res", c_vp),
         ("out", c_vp), ("workspace", c_vp), ("workspace_bytes", c_i64), ("n_splits", c_i32),
         ("partial", c_vp), ("prepared_codebook", c_vp),
+        ("k_out", c_i32), ("v_out", c_i32),
+        ("k_out_idx", c_vp), ("k_out_val", c_vp), ("k_out_head_stride", c_i64),
+        ("v_out_idx", c_vp), ("v_out_val", c_vp), ("v_out_head_stride", c_i64),
     ]
 
 
@@ -53,6 +56,10 @@ SIGNATURES = {
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "million_pq_decode": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, ctypes.c_int, c_i64,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "million_pq_outlier_split": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "million_pq_outlier_apply": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int, c_i64, c_i64,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "million_pq_codebook_prepared_bytes": (c_i64, [ctypes.c_int] * 3),
     "million_pq_codebook_prepare": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "million_pq_decode_attn_workspace_bytes": (c_i64, [ctypes.c_int] * 5),

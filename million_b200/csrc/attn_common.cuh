@@ -29,6 +29,10 @@ struct AttnArgs {
     int flat, flat_per, flat_ug;   // flat scheduling: CTA c owns 64-token units [c*flat_per, (c+1)*flat_per) of the (group, unit) space
     int units_per_split;  // 16-token units per split
     float scale_log2;     // log2(e)/sqrt(d)
+    // outlier side store (0 / nullptr = disabled): records (dim u8, delta io dtype) per coded token, head strides in records
+    int k_out, v_out;
+    const uint8_t* ko_idx; const void* ko_val; int64_t ko_head_stride;
+    const uint8_t* vo_idx; const void* vo_val; int64_t vo_head_stride;
     int dbg_mode;                     // hidden ablation switch (million_debug_set_mode): bit 0 skips QK gathers, bit 1 skips PV
     unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 64 words per CTA, see dbg_stamp
 };

@@ -54,7 +54,8 @@ int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, 
 
 // One segment = the coded tokens [t0, t1) of group (b, hk) (+ this CTA's share of the window), written as part `split` of
 // `np` parts of that group.
-template <typename T, int G, int VL>
+// OUT = 1: K-side outlier records (a.k_out <= 4 per token) are added to the scores; OUT = 0 is the plain path, untouched.
+template <typename T, int G, int VL, int OUT>
 __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint32_t* __restrict__ prepared, const int gsub, const int split,
                                                   const int hk, const int sub, const int b, const int t0, const int t1, const int np, const int piece) {
     using namespace fast;
@@ -227,11 +228,34 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             for (int g = 0; g < G; ++g) acc[sl][g] = __float2half2_rn(0.f);
         int since_flush = 0;
 
+        // K-side outlier records of my token in the NEXT tile, fetched one tile ahead (straight from HBM into registers)
+        uint32_t ko_dims = 0, ko_v01 = 0, ko_v23 = 0;
+        auto ko_fetch = [&](int tile) {
+            if constexpr (OUT) {
+                const int tok = t0 + tile * kTile + lane;
+                ko_dims = 0; ko_v01 = 0; ko_v23 = 0;
+                if (tile < n_tiles && tok < t1) {
+                    const int64_t rec = hb * a.ko_head_stride + (int64_t)tok * a.k_out;
+                    const unsigned short* vals = reinterpret_cast<const unsigned short*>(a.ko_val) + rec;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < a.k_out) {
+                            ko_dims |= (uint32_t)__ldg(a.ko_idx + rec + i) << (8 * i);
+                            const uint32_t hv = __ldg(vals + i);
+                            if (i < 2) ko_v01 |= hv << (16 * i); else ko_v23 |= hv << (16 * (i - 2));
+                        }
+                }
+            }
+        };
+        ko_fetch(warp);
+
         for (int tile = warp; tile < n_tiles; tile += kWarps) {
             cp_async_wait<1>();          // pending [K(i), V(i)] -> K(i) landed
             __syncwarp();
             const int tok = t0 + tile * kTile + lane;
             const bool valid = tok < t1;
+            const uint32_t my_dims = ko_dims, my_v01 = ko_v01, my_v23 = ko_v23;
+            ko_fetch(tile + kWarps);
 
             // ------------------------------------------------ QK: 64 conflict-free LUT gathers for my token
             float s[G];
@@ -279,6 +303,22 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                     if (!(a.dbg_mode & 1))
 #pragma unroll
                         for (int i = 0; i < kPer; ++i) qk_gathers(words[i], kf[i]);
+                }
+            }
+            if constexpr (OUT) {
+                // x_hat[dim] = centroid + delta: s_g += q_g[dim] * delta (q comes from L1: 256 B per head, read every tile).
+                // Records beyond k_out hold delta = 0 and dim = 0: they add nothing.
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < a.k_out) {
+                        const uint32_t pair = i < 2 ? my_v01 : my_v23;
+                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : (pair & 0xffffu));
+                        const float dv = io<T>::to_f(*reinterpret_cast<const T*>(&hv));
+                        const int dim = (my_dims >> (8 * i)) & 0xff;
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            s[g] = fmaf(io<T>::to_f(__ldg(reinterpret_cast<const T*>(a.q) + (int64_t)(b * a.nh + h0 + g) * 128 + dim)), dv, s[g]);
+                    }
                 }
             }
             __syncwarp();                                   // every lane has read its K row
@@ -550,13 +590,13 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
 }
 
 // VL = 0: value codes row-major (tokens x 64 bytes); VL = 1: transposed per sub-space (paged pool or (M, ld) rows)
-template <typename T, int G, int VL>
+template <typename T, int G, int VL, int OUT>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
     if (!a.flat) {
         // grid (splits, kv heads x 4-head sub-groups, batch): one segment per CTA
         int t0, t1;
         split_range(a, blockIdx.x, t0, t1);
-        attn_fast_segment<T, G, VL>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits, 0);
+        attn_fast_segment<T, G, VL, OUT>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits, 0);
         return;
     }
     // Flat scheduling: the (group, 64-token unit) space is cut into runs of equal COST, one per CTA, so every SM gets the
@@ -577,13 +617,13 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         const int first = (int)(real0 / per), last = (int)((real1 - 1) / per);
         const int us = (int)(s0 - real0), ue = (int)(s1 - real0);
         const int t1 = (ue * 64 < a.nk) ? ue * 64 : a.nk;
-        attn_fast_segment<T, G, VL>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1, piece++);
+        attn_fast_segment<T, G, VL, OUT>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1, piece++);
         __syncthreads();   // the next piece reuses every shared buffer
     }
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
-template <typename T, int G, int VL>
+template <typename T, int G, int VL, int OUT>
 static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
     const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + 256;
@@ -591,12 +631,12 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static bool configured = false;
     if (!configured) {
-        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G, VL, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
     if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
-    attn_fast_kernel<T, G, VL><<<grid, block, smem, stream>>>(a, prepared, gsub);
+    attn_fast_kernel<T, G, VL, OUT><<<grid, block, smem, stream>>>(a, prepared, gsub);
     MILLION_CUDA_OK(cudaGetLastError());
     return MILLION_OK;
 }
@@ -616,6 +656,8 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
         MILLION_UNSUPPORTED("fast decode attention: paged V needs page_size %% 32 == 0 and an aligned pool");
     if (a.nk > 0 && a.v_layout == MILLION_V_TRANSPOSED && ((a.v_ld & 15) || (a.v_head_stride & 15) || ((uintptr_t)a.v_codes & 15)))
         MILLION_UNSUPPORTED("fast decode attention: transposed V needs 16-byte aligned rows");
+    if (a.nk > 0 && a.v_out > 0) MILLION_UNSUPPORTED("fast decode attention: V-side outlier records run on the generic kernel");
+    if (a.nk > 0 && a.k_out > 0 && (a.k_out > 4 || dm4)) MILLION_UNSUPPORTED("fast decode attention: K-side outliers need k_out <= 4 and M = 64");
     if (!prepared) MILLION_UNSUPPORTED("fast decode attention needs a prepared codebook (million_pq_codebook_prepare)");
     if (a.nk > 0 && (((uintptr_t)a.k_codes | (uintptr_t)a.k_head_stride) & 15))
         MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");
@@ -645,7 +687,8 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     if (dm4) return launch_attn_fast_dm4(a, io_dtype, G, gsub, prepared, stream);
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
 #define MILLION_FAST_CASE(TT, GG) \
-    return a.v_layout == MILLION_V_ROWMAJOR ? launch_fast_t<TT, GG, 0>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1>(a, prep, gsub, stream)
+    return a.v_layout == MILLION_V_ROWMAJOR ? (a.k_out ? launch_fast_t<TT, GG, 0, 1>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 0, 0>(a, prep, gsub, stream)) \
+                                            : (a.k_out ? launch_fast_t<TT, GG, 1, 1>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1, 0>(a, prep, gsub, stream))
     if (io_dtype == MILLION_F16) {
         if (G == 4) MILLION_FAST_CASE(__half, 4);
         if (G == 2) MILLION_FAST_CASE(__half, 2);

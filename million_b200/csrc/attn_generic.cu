@@ -13,6 +13,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* lut = reinterpret_cast<float*>(smem_raw);  // M*C (coded splits) or d (window: q)
+    float* qs = lut + a.M * a.C;                      // coded splits with K outliers: q * scale, d floats
     __shared__ float P[128];
     __shared__ float red[33];
     __shared__ float mscr[kMergeScratch];
@@ -43,6 +44,8 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
                     acc = fmaf(io<T>::to_f(q[m * dm + k]), io<T>::to_f(kcent[(int64_t)i * dm + k]), acc);
                 lut[i] = acc * a.scale_log2;
             }
+            if (a.k_out)
+                for (int i = tid; i < a.d; i += 128) qs[i] = io<T>::to_f(q[i]) * a.scale_log2;
         }
         __syncthreads();
 
@@ -61,6 +64,11 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
                     const uint8_t* kc = a.k_codes + hb * a.k_head_stride + (int64_t)j * a.M;
                     float acc_s = 0.f;
                     for (int m = 0; m < a.M; ++m) acc_s += lut[m * a.C + kc[m]];
+                    if (a.k_out) {   // outlier side store: x_hat[dim] = centroid + delta
+                        const int64_t rec = hb * a.ko_head_stride + (int64_t)j * a.k_out;
+                        for (int i = 0; i < a.k_out; ++i)
+                            acc_s = fmaf(qs[a.ko_idx[rec + i]], io<T>::to_f(reinterpret_cast<const T*>(a.ko_val)[rec + i]), acc_s);
+                    }
                     s = acc_s;
                 }
             }
@@ -86,7 +94,13 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
                         const int m = i / dm, k = i % dm;
                         for (int jj = 0; jj < len; ++jj) {
                             const int code = v_code_at(a, hb, tile + jj, m);
-                            o = fmaf(P[jj], io<T>::to_f(vcent[((int64_t)m * a.C + code) * dm + k]), o);
+                            float vv = io<T>::to_f(vcent[((int64_t)m * a.C + code) * dm + k]);
+                            if (a.v_out) {
+                                const int64_t rec = hb * a.vo_head_stride + (int64_t)(tile + jj) * a.v_out;
+                                for (int i2 = 0; i2 < a.v_out; ++i2)
+                                    if (a.vo_idx[rec + i2] == i) vv += io<T>::to_f(reinterpret_cast<const T*>(a.vo_val)[rec + i2]);
+                            }
+                            o = fmaf(P[jj], vv, o);
                         }
                     }
                     acc[u] = o;
@@ -107,7 +121,7 @@ int launch_attn_generic(const AttnArgs& a_in, int io_dtype, cudaStream_t stream)
     AttnArgs a = a_in;
     a.n_parts = a.n_splits + 1;
     if (a.d > 256) MILLION_UNSUPPORTED("generic decode attention supports d <= 256 (got %d)", a.d);
-    const size_t smem = sizeof(float) * (size_t)max(a.M * a.C, a.d);
+    const size_t smem = sizeof(float) * (size_t)(a.M * a.C + a.d);
     dim3 grid(a.n_splits + 1, a.nh_k, a.bs), block(128);
     if (io_dtype == MILLION_F16) {
         MILLION_CUDA_OK(cudaFuncSetAttribute(attn_generic_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

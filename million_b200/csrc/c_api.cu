@@ -43,6 +43,10 @@ int launch_reconstruct(const void* codes, int code_bytes, int64_t chs, int64_t c
 int launch_rows_copy2(void* k_dst, void* v_dst, int64_t dst_hs_b, int64_t dst_off_b, const void* k_src, const void* v_src,
                       int64_t src_hs_b, int64_t src_off_b, int n_heads, int64_t bytes_per_head, cudaStream_t stream);
 int64_t encode_tc_prepared_bytes(int d, int M, int C);
+int launch_outlier_split(const void* x, int x_dtype, int64_t xhs, const float* cent, void* x_masked, uint8_t* out_idx, void* out_val,
+                         int64_t ohs, int64_t t0, int n_heads, int n_tokens, int d, int M, int C, int k_out, cudaStream_t stream);
+int launch_outlier_apply(void* out, int dtype, int64_t ohs, const uint8_t* idx, const void* val, int val_dtype, int64_t shs, int64_t t0,
+                         int n_heads, int n_tokens, int d, int k_out, cudaStream_t stream);
 int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C, void* out, cudaStream_t stream);
 int launch_encode_tc(const void* x, int x_dtype, int64_t xhs, const float* cent, const void* prepared, const CodeDst& dst,
                      int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream, bool probe_only);
@@ -129,6 +133,27 @@ int million_pq_decode(const void* codes, int code_bytes, int64_t chs, int64_t ct
                               (cudaStream_t)stream);
 }
 
+int million_pq_outlier_split(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, void* x_masked, uint8_t* out_idx,
+                             void* out_val, int64_t out_head_stride, int64_t t0, int n_heads, int n_tokens, int d, int M, int C,
+                             int k_out, million_stream_t stream) {
+    MILLION_REQUIRE(x && cent && x_masked && out_idx && out_val, "outlier_split: null pointer");
+    MILLION_REQUIRE(x_dtype == MILLION_F16 || x_dtype == MILLION_BF16, "outlier_split: x must be f16 or bf16");
+    MILLION_REQUIRE(n_heads >= 0 && n_tokens >= 0 && t0 >= 0, "outlier_split: bad sizes");
+    MILLION_REQUIRE(M > 0 && d % M == 0 && d % 32 == 0 && d <= 256 && d / M <= 16 && C > 1, "outlier_split: needs d %% 32 == 0, d <= 256, d/M <= 16 (d=%d M=%d)", d, M);
+    MILLION_REQUIRE(k_out >= 1 && k_out <= MILLION_MAX_OUTLIERS && k_out < d, "outlier_split: k_out must be in [1, %d]", MILLION_MAX_OUTLIERS);
+    return launch_outlier_split(x, x_dtype, x_head_stride, cent, x_masked, out_idx, out_val, out_head_stride, t0, n_heads, n_tokens, d, M, C,
+                                k_out, (cudaStream_t)stream);
+}
+
+int million_pq_outlier_apply(void* out, int dtype, int64_t out_head_stride, const uint8_t* idx, const void* val, int val_dtype,
+                             int64_t store_head_stride, int64_t t0, int n_heads, int n_tokens, int d, int k_out, million_stream_t stream) {
+    MILLION_REQUIRE(out && idx && val, "outlier_apply: null pointer");
+    MILLION_REQUIRE(dtype >= MILLION_F16 && dtype <= MILLION_F32 && (val_dtype == MILLION_F16 || val_dtype == MILLION_BF16), "outlier_apply: bad dtype");
+    MILLION_REQUIRE(n_heads >= 0 && n_tokens >= 0 && t0 >= 0 && d > 0 && k_out >= 1 && k_out <= MILLION_MAX_OUTLIERS, "outlier_apply: bad sizes");
+    return launch_outlier_apply(out, dtype, out_head_stride, idx, val, val_dtype, store_head_stride, t0, n_heads, n_tokens, d, k_out,
+                                (cudaStream_t)stream);
+}
+
 int64_t million_pq_codebook_prepared_bytes(int d, int M, int C) { return (d == 128 && (M == 64 || M == 32) && C == 256) ? 2 * 64 * 1024 : 0; }
 
 int million_pq_codebook_prepare(const void* k_cent, const void* v_cent, int dtype, int d, int M, int C, void* prepared,
@@ -213,6 +238,16 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     if (a.units_per_split < 4) a.units_per_split = 4;
     MILLION_REQUIRE(S + 1 <= 1024, "attn: at most 1023 splits");
     a.scale_log2 = kLog2e / sqrtf((float)p->d);
+    if (p->nk > 0 && p->k_out > 0 && p->k_out_idx && p->k_out_val) {
+        MILLION_REQUIRE(p->k_out <= MILLION_MAX_OUTLIERS && p->d <= 256, "attn: k_out %d > %d or d > 256", p->k_out, MILLION_MAX_OUTLIERS);
+        MILLION_REQUIRE(p->k_out_head_stride >= (int64_t)p->nk * p->k_out, "attn: k_out_head_stride too small");
+        a.k_out = p->k_out; a.ko_idx = p->k_out_idx; a.ko_val = p->k_out_val; a.ko_head_stride = p->k_out_head_stride;
+    }
+    if (p->nk > 0 && p->v_out > 0 && p->v_out_idx && p->v_out_val) {
+        MILLION_REQUIRE(p->v_out <= MILLION_MAX_OUTLIERS && p->d <= 256, "attn: v_out %d > %d or d > 256", p->v_out, MILLION_MAX_OUTLIERS);
+        MILLION_REQUIRE(p->v_out_head_stride >= (int64_t)p->nk * p->v_out, "attn: v_out_head_stride too small");
+        a.v_out = p->v_out; a.vo_idx = p->v_out_idx; a.vo_val = p->v_out_val; a.vo_head_stride = p->v_out_head_stride;
+    }
     a.dbg_timing = g_dbg_timing;
     a.dbg_mode = g_dbg_mode;
 

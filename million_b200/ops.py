@@ -132,6 +132,56 @@ def pq_decode(codes, cent):
     return out
 
 
+# ---------------------------------------------------------------------------------------------- outlier side store
+# Extension (the reference has no outlier code): semantics in DESIGN.md section 3.5.
+
+
+def outlier_split_into(X, cent_f32, idx_store, val_store, *, t0=0):
+    """Top-k_out |x| entries of every head-vector of X (bs, nh_k, n, d) -> records (dim, delta) written at token offset t0 of
+    idx_store (bs, nh_k, cap, k_out) uint8 / val_store (same shape, X's dtype).  Returns X with those entries zeroed — the
+    tensor to hand to pq_encode*()."""
+    _need_cuda(X, cent_f32, idx_store, val_store)
+    bs, nh, n, d = X.shape
+    M, C, dm = cent_f32.shape
+    k_out = idx_store.shape[3]
+    assert cent_f32.dtype == torch.float32 and cent_f32.is_contiguous() and M * dm == d
+    assert idx_store.dtype == torch.uint8 and val_store.dtype == X.dtype and idx_store.shape == val_store.shape
+    assert idx_store.shape[:2] == (bs, nh) and idx_store.stride(3) == 1 and idx_store.stride(2) == k_out
+    assert idx_store.stride() == val_store.stride() and (bs == 1 or idx_store.stride(0) == nh * idx_store.stride(1))
+    assert t0 + n <= idx_store.shape[2]
+    X, xhs = _x_view(X)
+    Xm = torch.empty(bs, nh, n, d, dtype=X.dtype, device=X.device)
+    L.check(L.lib().million_pq_outlier_split(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(Xm), _ptr(idx_store), _ptr(val_store),
+                                             idx_store.stride(1), t0, bs * nh, n, d, M, C, k_out, _stream(X)))
+    return Xm
+
+
+def pq_encode_outliers(X, cent_f32, k_out, *, impl=L.IMPL_AUTO):
+    """(codes (bs, nh_k, n, M) uint8, idx (bs, nh_k, n, k_out) uint8, val (bs, nh_k, n, k_out) X.dtype)."""
+    bs, nh, n, d = X.shape
+    idx = torch.empty(bs, nh, n, k_out, dtype=torch.uint8, device=X.device)
+    val = torch.empty(bs, nh, n, k_out, dtype=X.dtype, device=X.device)
+    Xm = outlier_split_into(X, cent_f32, idx, val)
+    return pq_encode(Xm, cent_f32, impl=impl), idx, val
+
+
+def outlier_apply(out, idx, val, *, t0=0):
+    """out (bs, nh_k, n, d) += side store records [t0, t0 + n): the reconstruction with outliers (in place)."""
+    _need_cuda(out, idx, val)
+    bs, nh, n, d = out.shape
+    k_out = idx.shape[3]
+    assert out.is_contiguous() and idx.dtype == torch.uint8 and idx.stride() == val.stride() and idx.stride(3) == 1 and idx.stride(2) == k_out
+    assert bs == 1 or idx.stride(0) == nh * idx.stride(1)
+    L.check(L.lib().million_pq_outlier_apply(_ptr(out), _dt(out), n * d, _ptr(idx), _ptr(val), _dt(val), idx.stride(1), t0,
+                                             bs * nh, n, d, k_out, _stream(out)))
+    return out
+
+
+def pq_decode_outliers(codes, cent, idx, val):
+    """sa_decode_4d + the side store: (bs, nh_k, n, d) in cent's dtype."""
+    return outlier_apply(pq_decode(codes, cent), idx, val)
+
+
 # ---------------------------------------------------------------------------------------------- attention
 
 _workspaces = {}
@@ -176,12 +226,13 @@ def prepare_codebooks(k_cent, v_cent):
 
 def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=None, v_layout=L.V_ROWMAJOR,
                    v_page_ids=None, page_size=0, out=None, partial=None, n_splits=0, impl=L.IMPL_AUTO, workspace=None,
-                   prepared=None):
+                   prepared=None, k_outliers=None, v_outliers=None):
     """One decode-attention call (include/million_b200.h: million_pq_decode_attn).
 
     q (bs, nh, 1, d) | (bs, nh, d); k_codes (bs, nh_k, >=nk, M) uint8 (head stride taken from the tensor);
     v_codes: rowmajor (bs, nh_k, >=nk, M) | transposed (bs, nh_k, M, >=nk) | paged pool (pages, M, page_size);
     k_res/v_res (bs, nh_k, Lt, d).  Returns (bs, nh, 1, d) in q's dtype, or fills `partial` (bs, nh, d+2) fp32.
+    k_outliers / v_outliers: optional (idx, val) side stores (bs, nh_k, >=nk, k_out) uint8 / q's dtype (extension).
     """
     _need_cuda(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res)
     bs, nh = q.shape[0], q.shape[1]
@@ -212,6 +263,21 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
             assert v_codes.is_contiguous() and v_page_ids.dtype == torch.int64 and v_page_ids.is_contiguous()
             p.v_page_ids, p.n_pages, p.page_size = v_page_ids.data_ptr(), v_page_ids.shape[2], page_size or v_codes.shape[2]
     p.v_layout = v_layout
+    if nk:
+        for side, store in (("k", k_outliers), ("v", v_outliers)):
+            if store is None:
+                continue
+            idx, val = store
+            _need_cuda(idx, val)
+            ko = idx.shape[3]
+            assert idx.dtype == torch.uint8 and val.dtype == q.dtype and idx.stride() == val.stride()
+            assert idx.stride(3) == 1 and idx.stride(2) == ko and idx.shape[2] >= nk
+            assert bs == 1 or idx.stride(0) == nh_k * idx.stride(1)
+            hs = idx.stride(1) if nh_k > 1 or bs > 1 else idx.shape[2] * ko
+            if side == "k":
+                p.k_out, p.k_out_idx, p.k_out_val, p.k_out_head_stride = ko, idx.data_ptr(), val.data_ptr(), hs
+            else:
+                p.v_out, p.v_out_idx, p.v_out_val, p.v_out_head_stride = ko, idx.data_ptr(), val.data_ptr(), hs
     p.k_cent, p.v_cent = k_cent.data_ptr(), v_cent.data_ptr()
     if impl != L.IMPL_GENERIC:
         if prepared is None:

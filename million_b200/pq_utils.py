@@ -186,6 +186,30 @@ class _CodeStore:
         return self.buf[:, :, :, :n] if self.transposed else self.buf[:, :, :n]
 
 
+class _OutlierStore:
+    """Side store of one layer and one of K/V: (dim uint8, delta fp16/bf16) records, (bs, nh_k, cap, k_out), grown with
+    the code store it belongs to.  Extension — the reference has no outlier code."""
+
+    def __init__(self, bs, nh_k, k_out, val_dtype, device):
+        self.bs, self.nh_k, self.k_out, self.val_dtype, self.device = bs, nh_k, k_out, val_dtype, device
+        self.cap = 0
+        self.idx = torch.zeros((bs, nh_k, 0, k_out), dtype=torch.uint8, device=device)
+        self.val = torch.zeros((bs, nh_k, 0, k_out), dtype=val_dtype, device=device)
+
+    def reserve(self, cap, keep):
+        if cap <= self.cap:
+            return
+        idx = torch.zeros((self.bs, self.nh_k, cap, self.k_out), dtype=torch.uint8, device=self.device)
+        val = torch.zeros((self.bs, self.nh_k, cap, self.k_out), dtype=self.val_dtype, device=self.device)
+        if keep:
+            idx[:, :, :keep] = self.idx[:, :, :keep]
+            val[:, :, :keep] = self.val[:, :, :keep]
+        self.idx, self.val, self.cap = idx, val, cap
+
+    def view(self, n):
+        return self.idx[:, :, :n], self.val[:, :, :n]
+
+
 class DynamicPQCache(metaclass=Singleton):
     """pq_utils.py:98-408.  Same constructor, attributes and methods.
 
@@ -194,8 +218,13 @@ class DynamicPQCache(metaclass=Singleton):
     that filled it; the next step only waits on an event.  Results are identical either way."""
 
     def __init__(self, *, bs, nh, num_key_value_heads, M, layer_num, dtype=torch.uint8, nbits=8, d=128,
-                 scalar_t=torch.float32, async_flush=True, device='cuda'):
+                 scalar_t=torch.float32, async_flush=True, device='cuda', outliers=(0, 0)):
+        """`outliers=(k_out_K, k_out_V)` (extension, default off): that many largest-|x| entries of every key / value vector
+        bypass PQ and are kept as (dim, delta) records; see DESIGN.md section 3.5 for the exact semantics."""
         self.bs, self.nh, self.num_key_value_heads, self.M = bs, nh, num_key_value_heads, M
+        self.k_out, self.v_out = (int(outliers), int(outliers)) if isinstance(outliers, int) else (int(outliers[0]), int(outliers[1]))
+        if (self.k_out or self.v_out) and scalar_t not in (torch.float16, torch.bfloat16):
+            raise ValueError("the outlier side store needs scalar_t float16 or bfloat16")
         self.layer_num, self.dtype, self.nbits, self.d, self.scalar_t = layer_num, dtype, nbits, d, scalar_t
         self.device = torch.device(device)
         self.async_flush = async_flush
@@ -214,6 +243,9 @@ class DynamicPQCache(metaclass=Singleton):
             raise RuntimeError("DynamicPQCache needs a CUDA device (no CPU path)")
         self._k = [self._new_store() for _ in range(self.layer_num)]
         self._v = [self._new_store() for _ in range(self.layer_num)]
+        mk = lambda ko: [_OutlierStore(self.bs, self.num_key_value_heads, ko, self.scalar_t, self.device) if ko else None
+                         for _ in range(self.layer_num)]
+        self._ko, self._vo = mk(self.k_out), mk(self.v_out)
         z = lambda: torch.zeros((self.bs, self.num_key_value_heads, self.max_residual_length, self.d),
                                 dtype=self.scalar_t, device=self.device)
         self.key_residual_cache = [z() for _ in range(self.layer_num)]
@@ -252,16 +284,46 @@ class DynamicPQCache(metaclass=Singleton):
         return self._kc_attn, self._vc_attn
 
     # ---- code append
+    def _reserve(self, layer_idx, n):
+        ks, vs = self._k[layer_idx], self._v[layer_idx]
+        ks.reserve(ks.len + n)
+        vs.reserve(vs.len + n)
+        if self._ko[layer_idx] is not None:
+            self._ko[layer_idx].reserve(ks.cap, ks.len)
+        if self._vo[layer_idx] is not None:
+            self._vo[layer_idx].reserve(vs.cap, vs.len)
+
+    def _encode_kv(self, key_states, value_states, layer_idx):
+        """Encode at the current end of the stores (which must already be reserved); with the side store on, the outliers are
+        split off first and the encoder sees the masked vectors."""
+        ks, vs = self._k[layer_idx], self._v[layer_idx]
+        ko, vo = self._ko[layer_idx], self._vo[layer_idx]
+        if ko is not None:
+            key_states = ops.outlier_split_into(key_states, self._key_cent_f32, ko.idx, ko.val, t0=ks.len)
+        if vo is not None:
+            value_states = ops.outlier_split_into(value_states, self._value_cent_f32, vo.idx, vo.val, t0=vs.len)
+        ops.pq_encode_into(key_states, self._key_cent_f32, ks.buf, t0=ks.len)
+        ops.pq_encode_into(value_states, self._value_cent_f32, vs.buf, t0=vs.len,
+                           layout="transposed" if vs.transposed else "rowmajor")
+
+    def _reconstruct(self, layer_idx, which, n_last=None, dtype=None):
+        """sa_decode_4d of the last n_last (default: all) tokens of a store, side store applied."""
+        st, cent, out = (self._k, self.key_cent, self._ko) if which == 'k' else (self._v, self.value_cent, self._vo)
+        st, out = st[layer_idx], out[layer_idx]
+        n = st.len if n_last is None else n_last
+        codes = st.view()[:, :, :, st.len - n:].transpose(2, 3) if st.transposed else st.view()[:, :, st.len - n:]
+        x = sa_decode_4d(codes, cent if dtype is None else cent.to(dtype))
+        if out is not None and n:
+            ops.outlier_apply(x, out.idx, out.val, t0=st.len - n)
+        return x
+
     def _encode_append(self, key_states, value_states, layer_idx, count_seen=True):
         if self._pending[layer_idx] is not None:
             self._finish_async_flush(layer_idx)
         n = key_states.size(2)
         ks, vs = self._k[layer_idx], self._v[layer_idx]
-        ks.reserve(ks.len + n)
-        vs.reserve(vs.len + n)
-        ops.pq_encode_into(key_states, self._key_cent_f32, ks.buf, t0=ks.len)
-        ops.pq_encode_into(value_states, self._value_cent_f32, vs.buf, t0=vs.len,
-                           layout="transposed" if vs.transposed else "rowmajor")
+        self._reserve(layer_idx, n)
+        self._encode_kv(key_states, value_states, layer_idx)
         ks.len += n
         vs.len += n
         if count_seen:
@@ -289,10 +351,10 @@ class DynamicPQCache(metaclass=Singleton):
         past_length = self._k[layer_idx].len
         if distort_recent:
             self._encode_append(key_states, value_states, layer_idx)
-            return sa_decode_4d(self.key_cache[layer_idx], self.key_cent), sa_decode_4d(self.value_cache[layer_idx], self.value_cent)
+            return self._reconstruct(layer_idx, 'k'), self._reconstruct(layer_idx, 'v')
         if past_length > 0:
-            past_key_states = sa_decode_4d(self.key_cache[layer_idx], self.key_cent)
-            past_value_states = sa_decode_4d(self.value_cache[layer_idx], self.value_cent)
+            past_key_states = self._reconstruct(layer_idx, 'k')
+            past_value_states = self._reconstruct(layer_idx, 'v')
         self._encode_append(key_states, value_states, layer_idx)
         if past_length > 0:
             key_states = torch.cat([past_key_states.to(key_states.dtype), key_states], dim=2)
@@ -311,10 +373,8 @@ class DynamicPQCache(metaclass=Singleton):
         n = key_states.size(2)
         self._encode_append(key_states, value_states, layer_idx)
         if distort_recent is True:
-            ks, vs = self._k[layer_idx], self._v[layer_idx]
-            key_states = sa_decode_4d(ks.view()[:, :, ks.len - n:], self.key_cent.to(key_states.dtype))
-            vview = vs.view()[:, :, :, vs.len - n:].transpose(2, 3) if vs.transposed else vs.view()[:, :, vs.len - n:]
-            value_states = sa_decode_4d(vview, self.value_cent.to(value_states.dtype))
+            key_states = self._reconstruct(layer_idx, 'k', n, key_states.dtype)
+            value_states = self._reconstruct(layer_idx, 'v', n, value_states.dtype)
         return self._prefill_attention(query_states, key_states, value_states)
 
     def residual_attention(self, query_states, layer_idx):
@@ -344,16 +404,12 @@ class DynamicPQCache(metaclass=Singleton):
     def _start_async_flush(self, layer_idx, n):
         """Launch the flush of a full window on the side stream; the code stores are grown on the main stream
         first so the side stream never allocates memory the main stream is using."""
-        ks, vs = self._k[layer_idx], self._v[layer_idx]
-        ks.reserve(ks.len + n)
-        vs.reserve(vs.len + n)
+        self._reserve(layer_idx, n)
         main = torch.cuda.current_stream(self.device)
         side = self._side_stream()
         side.wait_stream(main)                      # window rows are complete, caches are allocated
         with torch.cuda.stream(side):
-            ops.pq_encode_into(self.key_residual_cache[layer_idx][:, :, :n], self._key_cent_f32, ks.buf, t0=ks.len)
-            ops.pq_encode_into(self.value_residual_cache[layer_idx][:, :, :n], self._value_cent_f32, vs.buf, t0=vs.len,
-                               layout="transposed" if vs.transposed else "rowmajor")
+            self._encode_kv(self.key_residual_cache[layer_idx][:, :, :n], self.value_residual_cache[layer_idx][:, :, :n], layer_idx)
             ev = torch.cuda.Event()
             ev.record(side)
         self._pending[layer_idx] = (ev, n)
@@ -388,8 +444,19 @@ class DynamicPQCache(metaclass=Singleton):
         self.residualed_tokens[layer_idx] += n
         self.seen_tokens[layer_idx] += n
 
-        kernel = self.registery.get_kernel(l=self.seen_tokens[layer_idx])
         kc, vc = self._attn_cents(query_states.dtype)
+        if self.k_out or self.v_out:
+            # the reference's 10-argument kernel signature (pq_utils.py:83-94) has no place for the side store
+            ks = self._k[layer_idx]
+            out = ops.pq_decode_attn(query_states, ks.view(), self._v[layer_idx].view(), kc, vc,
+                                     self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
+                                     self.residualed_tokens[layer_idx],
+                                     k_outliers=self._ko[layer_idx].view(ks.len) if self.k_out else None,
+                                     v_outliers=self._vo[layer_idx].view(ks.len) if self.v_out else None)
+            if self.async_flush and self.residualed_tokens[layer_idx] == self.max_residual_length:
+                self._start_async_flush(layer_idx, self.max_residual_length)
+            return out
+        kernel = self.registery.get_kernel(l=self.seen_tokens[layer_idx])
         out = kernel(query_states, self._k[layer_idx].view(), self._v[layer_idx].view(), kc, vc,
                      self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
                      self.residualed_tokens[layer_idx])
@@ -446,6 +513,12 @@ class DynamicPQCache(metaclass=Singleton):
         if ks.len:
             p.k_codes, p.k_head_stride = ks.buf.data_ptr(), ks.cap * self.M
             self._fill_v(p, layer_idx)
+            if self.k_out:
+                ko = self._ko[layer_idx]
+                p.k_out, p.k_out_idx, p.k_out_val, p.k_out_head_stride = self.k_out, ko.idx.data_ptr(), ko.val.data_ptr(), ko.cap * self.k_out
+            if self.v_out:
+                vo = self._vo[layer_idx]
+                p.v_out, p.v_out_idx, p.v_out_val, p.v_out_head_stride = self.v_out, vo.idx.data_ptr(), vo.val.data_ptr(), vo.cap * self.v_out
         st = plan['attn'](plan['ref'], stream)
         if st:
             L.check(st)
@@ -455,6 +528,12 @@ class DynamicPQCache(metaclass=Singleton):
     @property
     def pq_cache_size(self):
         return sum(s.len * self.bs * self.num_key_value_heads * self.M * s.buf.element_size() for s in self._k + self._v)
+
+    @property
+    def outlier_store_size(self):
+        """bytes of (dim, delta) records held for the tokens quantized so far (extension)."""
+        per_tok = self.bs * self.num_key_value_heads * 3
+        return sum(s.len for s in self._k) * per_tok * self.k_out + sum(s.len for s in self._v) * per_tok * self.v_out
 
     @property
     def codebook_size(self):

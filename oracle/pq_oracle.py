@@ -301,26 +301,82 @@ def gather_pages(pool, table, T: int) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
-# A.6 outlier side store — OUR definition, no reference counterpart (parity unpinned)
+# A.6 outlier side store — OUR definition, no reference counterpart (parity unpinned: the reference has no
+# outlier code at all; these functions are checked only against themselves and the kernels)
+#
+#   1. outliers of a head-vector x = its k_out entries of largest |x| (fp32), ties -> lowest dim; listed in that order
+#   2. x' = x with those entries zeroed; codes = pq_encode(x') (A.2, unchanged)
+#   3. delta_i = round_to_io( fp32(x[dim_i]) - C[m_i, code[m_i], k_i] )          (C fp32, the encoder's codebook)
+#   4. reconstruction  x_hat = pq_decode(codes, C) ; x_hat[dim_i] += delta_i
+#   5. decode attention uses x_hat for K and V:  s_j += scale * sum_i q[kdim_i] * kdelta_i,
+#                                                o   += sum_j p_j * sum_i vdelta_i * e[vdim_i]
+# Side store layout: idx (bs, nh_k, n, k_out) uint8, val (bs, nh_k, n, k_out) io dtype.  k_out = 0 is the plain path.
 
 
-def outlier_split(X, k_out: int, tau: float):
-    """Per head-vector keep up to `k_out` entries with |x| > tau * rms(x), largest first (ties: lowest
-    dim).  Returns (X_dense with those entries zeroed, mask bool same shape)."""
+def outlier_select(X, k_out: int) -> np.ndarray:
+    """(…, d) -> (…, k_out) uint8: dims of the k_out largest |x|, largest first, ties -> lowest dim."""
+    a = np.abs(_f32(X))
+    order = np.argsort(-a, axis=-1, kind='stable')              # stable: equal |x| keep ascending dim order
+    return order[..., :k_out].astype(np.uint8)
+
+
+def pq_encode_outliers(X, C, k_out: int, io_dtype=np.float16, out_dtype=np.uint8):
+    """Returns (codes (bs,nh,n,M), idx (bs,nh,n,k_out) uint8, val (bs,nh,n,k_out) io_dtype)."""
     X = _f32(X)
-    rms = np.sqrt((X.astype(np.float64) ** 2).mean(-1, keepdims=True)).astype(np.float32)
-    a = np.abs(X)
-    cand = a > (np.float32(tau) * rms)
-    order = np.argsort(-a, axis=-1, kind='stable')
-    rank = np.empty_like(order)
-    np.put_along_axis(rank, order, np.arange(X.shape[-1])[None].repeat(int(np.prod(X.shape[:-1])), 0).reshape(X.shape), axis=-1)
-    mask = cand & (rank < k_out)
-    return np.where(mask, np.float32(0), X), mask
+    C = _f32(C)
+    M, c, d_m = C.shape
+    idx = outlier_select(X, k_out)
+    Xm = X.copy()
+    np.put_along_axis(Xm, idx.astype(np.int64), np.float32(0), axis=-1)
+    codes = pq_encode(Xm, C, out_dtype)
+    ii = idx.astype(np.int64)
+    m_i, k_i = ii // d_m, ii % d_m
+    code_i = np.take_along_axis(codes.astype(np.int64), m_i, axis=-1)
+    cval = C[m_i, code_i, k_i]                                  # fp32
+    xval = np.take_along_axis(X, ii, axis=-1)
+    val = (xval - cval).astype(np.float32)
+    return codes, idx, _round_io(val, io_dtype)
 
 
-def pq_reconstruct_with_outliers(codes, C, X, mask):
-    xh = _f32(pq_decode(codes, _f32(C)))
-    return np.where(mask, _f32(X), xh)
+def _round_io(a, io_dtype):
+    if io_dtype == 'bf16':
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+    return np.asarray(a, dtype=np.float32).astype(io_dtype)
+
+
+def pq_decode_outliers(codes, C, idx, val) -> np.ndarray:
+    """fp32 reconstruction with the side store applied (step 4)."""
+    xh = _f32(pq_decode(codes, _f32(C))).copy()
+    ii = np.asarray(idx).astype(np.int64)
+    if ii.shape[-1]:
+        cur = np.take_along_axis(xh, ii, axis=-1)
+        np.put_along_axis(xh, ii, cur + _f32(val), axis=-1)     # dims of one vector are distinct: no collisions
+    return xh
+
+
+def pq_decode_attn_outliers(q, Kc, Vc, Kcent, Vcent, Kres, Vres, r, kout=None, vout=None):
+    """fp32 decode attention on the reconstruction with outliers (step 5); kout/vout = (idx, val) or None."""
+    q32 = _f32(q)
+    if q32.ndim == 4:
+        q32 = q32[:, :, 0, :]
+    bs, nh, d = q32.shape
+    Kc = np.asarray(Kc)
+    nh_k, nk = Kc.shape[1], Kc.shape[2]
+    G = nh // nh_k
+    Khat = pq_decode_outliers(Kc, Kcent, *kout) if kout is not None else _f32(pq_decode(Kc, _f32(Kcent)))
+    Vhat = pq_decode_outliers(Vc, Vcent, *vout) if vout is not None else _f32(pq_decode(Vc, _f32(Vcent)))
+    scale = np.float32(1.0 / math.sqrt(d))
+    out = np.empty((bs, nh, 1, d), dtype=np.float32)
+    for b in range(bs):
+        for h in range(nh):
+            hk = h // G
+            K = np.concatenate([Khat[b, hk], _f32(Kres)[b, hk, :r]], axis=0)
+            V = np.concatenate([Vhat[b, hk], _f32(Vres)[b, hk, :r]], axis=0)
+            s = (K @ q32[b, h]) * scale
+            p = np.exp(s - s.max())
+            out[b, h, 0] = (p @ V) / p.sum(dtype=np.float32)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

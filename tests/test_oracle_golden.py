@@ -119,3 +119,41 @@ def test_c_oracle_agrees_with_numpy_oracle_and_golden(golden):
         g = lambda k: golden[f"att{i}_{k}"]
         got = CO.pq_decode_attn(g("q"), g("kc"), g("vc"), g("kcent"), g("vcent"), g("kres"), g("vres"), int(g("shape")[4]))
         np.testing.assert_allclose(got, g("out"), atol=3e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ outlier side store
+# (extension; no reference counterpart: these pin the oracle's own definition, section A.6 of oracle/pq_oracle.py)
+
+
+def test_outlier_oracle_definition():
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((1, 2, 40, 128)).astype(np.float16)
+    X[..., 3] = 40.0
+    C = rng.standard_normal((64, 256, 2)).astype(np.float16).astype(np.float32)
+    codes, idx, val = O.pq_encode_outliers(X, C, 2)
+    assert idx.shape == (1, 2, 40, 2) and idx.dtype == np.uint8 and val.dtype == np.float16
+    assert (idx[..., 0] == 3).all()                                   # the spiked channel is always the largest
+    # codes are the plain encoder's codes of the masked vectors
+    Xm = X.astype(np.float32).copy()
+    np.put_along_axis(Xm, idx.astype(np.int64), 0.0, axis=-1)
+    assert np.array_equal(codes, O.pq_encode(Xm, C))
+    # outlier dims are reconstructed to fp16 rounding of the delta, other dims exactly as plain PQ of the masked vector
+    xh = O.pq_decode_outliers(codes, C, idx, val)
+    at = np.take_along_axis(xh, idx.astype(np.int64), -1) - np.take_along_axis(X.astype(np.float32), idx.astype(np.int64), -1)
+    assert np.abs(at).max() <= 2.0 ** -5                              # |delta| < 64 -> half an fp16 ulp <= 2^-5
+    rest = xh.copy(); base = O.pq_decode(codes, C).copy()
+    np.put_along_axis(rest, idx.astype(np.int64), 0.0, -1); np.put_along_axis(base, idx.astype(np.int64), 0.0, -1)
+    assert np.array_equal(rest, base)
+    # k_out = 0: the plain path
+    c0, i0, v0 = O.pq_encode_outliers(X, C, 0)
+    assert np.array_equal(c0, O.pq_encode(X, C)) and i0.shape[-1] == 0
+    assert np.array_equal(O.pq_decode_outliers(c0, C, i0, v0), O.pq_decode(c0, C))
+
+
+def test_outlier_oracle_attention_reduces_to_plain():
+    inp = O.make_inputs(bs=1, nh=4, nh_k=2, nk=200, seed=3)
+    a = O.pq_decode_attn(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], 9)
+    zi = np.zeros((1, 2, 200, 2), np.uint8); zv = np.zeros((1, 2, 200, 2), np.float16)
+    b = O.pq_decode_attn_outliers(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], 9,
+                                  kout=(zi, zv), vout=(zi, zv))
+    np.testing.assert_allclose(a, b, atol=2e-6, rtol=1e-5)
