@@ -66,7 +66,6 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
     unsigned char* stage_p = smem + kStageOff;                           // kWarps * (K tile + V tile)
     unsigned char* pbuf_p = smem + kPbufOff;                             // kWarps * kTile * 8 bytes (4 halves per token)
     int* flag = reinterpret_cast<int*>(smem + kMiscOff);
-    float* red = reinterpret_cast<float*>(smem + kMiscOff + 16);         // 33 floats
     // after the main loop the stage buffers and p slots are dead: reuse them for the cross-warp combine and the merge
     float* xch = reinterpret_cast<float*>(stage_p);                      // 2 * kWarps * G * 130 floats, then kMergeScratch
 
@@ -212,6 +211,13 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             }
         }
         cp_async_wait<2>();    // pending: [V table, K(0), V(0)] -> my part of the V table has landed
+        if constexpr (OUT) {
+            // q as a [dim][head] table for the outlier terms.  It takes the whole misc area (with G = 4 this kernel then uses
+            // exactly 227 KB); the ticket flag and the merge mbarrier in there are only touched after the main loop.
+            T* qt = reinterpret_cast<T*>(smem + kMiscOff);
+            for (int i = tid; i < 128 * G; i += kThreads)
+                qt[i] = reinterpret_cast<const T*>(a.q)[(int64_t)(b * a.nh + h0 + (i % G)) * 128 + i / G];
+        }
     }
     __syncthreads();
     dbg_stamp(a, 1, piece);
@@ -229,21 +235,29 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         int since_flush = 0;
 
         // K-side outlier records of my token in the NEXT tile, fetched one tile ahead (straight from HBM into registers)
+        // Raw load results only: nothing consumes them before the next iteration (a shift or an OR here would make this warp wait
+        // for the HBM round trip on the spot).  k_out 1, 2, 4: one vector load each for dims and deltas; 3: byte-wise.
         uint32_t ko_dims = 0, ko_v01 = 0, ko_v23 = 0;
         auto ko_fetch = [&](int tile) {
             if constexpr (OUT) {
                 const int tok = t0 + tile * kTile + lane;
-                ko_dims = 0; ko_v01 = 0; ko_v23 = 0;
-                if (tile < n_tiles && tok < t1) {
-                    const int64_t rec = hb * a.ko_head_stride + (int64_t)tok * a.k_out;
-                    const unsigned short* vals = reinterpret_cast<const unsigned short*>(a.ko_val) + rec;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (i < a.k_out) {
-                            ko_dims |= (uint32_t)__ldg(a.ko_idx + rec + i) << (8 * i);
-                            const uint32_t hv = __ldg(vals + i);
-                            if (i < 2) ko_v01 |= hv << (16 * i); else ko_v23 |= hv << (16 * (i - 2));
-                        }
+                const bool ok = tile < n_tiles && tok < t1;
+                const int64_t rec = hb * a.ko_head_stride + (int64_t)(ok ? tok : t0) * a.k_out;
+                const unsigned short* vals = reinterpret_cast<const unsigned short*>(a.ko_val) + rec;
+                if (a.k_out == 2) {
+                    ko_dims = __ldg(reinterpret_cast<const unsigned short*>(a.ko_idx + rec));
+                    ko_v01 = __ldg(reinterpret_cast<const uint32_t*>(vals));
+                } else if (a.k_out == 4) {
+                    ko_dims = __ldg(reinterpret_cast<const uint32_t*>(a.ko_idx + rec));
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(vals));
+                    ko_v01 = v.x; ko_v23 = v.y;
+                } else if (a.k_out == 1) {
+                    ko_dims = __ldg(a.ko_idx + rec);
+                    ko_v01 = __ldg(vals);
+                } else {
+                    ko_dims = (uint32_t)__ldg(a.ko_idx + rec) | ((uint32_t)__ldg(a.ko_idx + rec + 1) << 8) | ((uint32_t)__ldg(a.ko_idx + rec + 2) << 16);
+                    ko_v01 = (uint32_t)__ldg(vals) | ((uint32_t)__ldg(vals + 1) << 16);
+                    ko_v23 = __ldg(vals + 2);
                 }
             }
         };
@@ -306,20 +320,27 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 }
             }
             if constexpr (OUT) {
-                // x_hat[dim] = centroid + delta: s_g += q_g[dim] * delta (q comes from L1: 256 B per head, read every tile).
-                // Records beyond k_out hold delta = 0 and dim = 0: they add nothing.
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 4; ++i)
                     if (i < a.k_out) {
                         const uint32_t pair = i < 2 ? my_v01 : my_v23;
                         const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : (pair & 0xffffu));
-                        const float dv = io<T>::to_f(*reinterpret_cast<const T*>(&hv));
+                        const float dv = valid ? io<T>::to_f(*reinterpret_cast<const T*>(&hv)) : 0.f;
+                        // q_g[dim] for the G heads from the [dim][head] table in shared memory (one load)
                         const int dim = (my_dims >> (8 * i)) & 0xff;
-#pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            s[g] = fmaf(io<T>::to_f(__ldg(reinterpret_cast<const T*>(a.q) + (int64_t)(b * a.nh + h0 + g) * 128 + dim)), dv, s[g]);
+                        const unsigned char* qrow = smem + kMiscOff + dim * (2 * G);
+                        if constexpr (G == 4) {
+                            const uint2 w = *reinterpret_cast<const uint2*>(qrow);
+                            const float2 q01 = io<T>::to_f2(w.x), q23 = io<T>::to_f2(w.y);
+                            s[0] = fmaf(q01.x, dv, s[0]); s[1] = fmaf(q01.y, dv, s[1]);
+                            s[2] = fmaf(q23.x, dv, s[2]); s[3] = fmaf(q23.y, dv, s[3]);
+                        } else if constexpr (G == 2) {
+                            const float2 q01 = io<T>::to_f2(*reinterpret_cast<const uint32_t*>(qrow));
+                            s[0] = fmaf(q01.x, dv, s[0]); s[1] = fmaf(q01.y, dv, s[1]);
+                        } else {
+                            s[0] = fmaf(io<T>::to_f(*reinterpret_cast<const T*>(qrow)), dv, s[0]);
+                        }
                     }
-                }
             }
             __syncwarp();                                   // every lane has read its K row
             issue(tile + kWarps, kbase, ks_s);              // K(i+1) streams in during the PV phase
@@ -626,7 +647,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
 template <typename T, int G, int VL, int OUT>
 static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
-    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + 256;
+    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + (OUT ? 1024 : 256);
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= 2 * kWarps * 4 * 130 * sizeof(float), "stage + p area too small for the combine");
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static bool configured = false;
@@ -657,7 +678,10 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     if (a.nk > 0 && a.v_layout == MILLION_V_TRANSPOSED && ((a.v_ld & 15) || (a.v_head_stride & 15) || ((uintptr_t)a.v_codes & 15)))
         MILLION_UNSUPPORTED("fast decode attention: transposed V needs 16-byte aligned rows");
     if (a.nk > 0 && a.v_out > 0) MILLION_UNSUPPORTED("fast decode attention: V-side outlier records run on the generic kernel");
-    if (a.nk > 0 && a.k_out > 0 && (a.k_out > 4 || dm4)) MILLION_UNSUPPORTED("fast decode attention: K-side outliers need k_out <= 4 and M = 64");
+    if (a.nk > 0 && a.k_out > 4) MILLION_UNSUPPORTED("fast decode attention: K-side outliers need k_out <= 4");
+    if (a.nk > 0 && a.k_out > 0 && a.k_out != 3 &&
+        ((uintptr_t)a.ko_idx % a.k_out || a.ko_head_stride % a.k_out || (uintptr_t)a.ko_val % (2 * a.k_out)))
+        MILLION_UNSUPPORTED("fast decode attention: the K-side outlier store must be aligned to one token's records");
     if (!prepared) MILLION_UNSUPPORTED("fast decode attention needs a prepared codebook (million_pq_codebook_prepare)");
     if (a.nk > 0 && (((uintptr_t)a.k_codes | (uintptr_t)a.k_head_stride) & 15))
         MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");

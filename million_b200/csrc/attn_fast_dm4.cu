@@ -46,7 +46,7 @@ int launch_codebook_prepare_dm4(const void* kcent, const void* vcent, int io_dty
 }
 
 // One segment = the coded tokens [t0, t1) of group (b, hk) (+ this CTA's share of the window), part `split` of `np`.
-template <typename T, int G>
+template <typename T, int G, int OUT>
 __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32_t* __restrict__ prepared, const int gsub, const int split,
                                                  const int hk, const int sub, const int b, const int t0, const int t1, const int np) {
     using namespace fast;
@@ -115,6 +115,12 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             }
             __syncthreads();
             if (ch + 2 < 4) load_chunk(ch + 2);
+        }
+        if constexpr (OUT) {
+            // q as a [dim][head] table for the outlier terms (misc area; flag and merge scratch there are used after the loop)
+            T* qt = reinterpret_cast<T*>(smem + kMiscOff);
+            for (int i = tid; i < 128 * G; i += kThreads)
+                qt[i] = reinterpret_cast<const T*>(a.q)[(int64_t)(b * a.nh + h0 + (i % G)) * 128 + i / G];
         }
     }
     __syncthreads();
@@ -198,11 +204,42 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
         };
         int since_flush = 0;
 
+        // K-side outlier records of my token in the NEXT tile, fetched one tile ahead (see attn_fast.cu)
+        // Raw load results only: nothing consumes them before the next iteration (a shift or an OR here would make this warp wait
+        // for the HBM round trip on the spot).  k_out 1, 2, 4: one vector load each for dims and deltas; 3: byte-wise.
+        uint32_t ko_dims = 0, ko_v01 = 0, ko_v23 = 0;
+        auto ko_fetch = [&](int tile) {
+            if constexpr (OUT) {
+                const int tok = t0 + tile * kTile + lane;
+                const bool ok = tile < n_tiles && tok < t1;
+                const int64_t rec = hb * a.ko_head_stride + (int64_t)(ok ? tok : t0) * a.k_out;
+                const unsigned short* vals = reinterpret_cast<const unsigned short*>(a.ko_val) + rec;
+                if (a.k_out == 2) {
+                    ko_dims = __ldg(reinterpret_cast<const unsigned short*>(a.ko_idx + rec));
+                    ko_v01 = __ldg(reinterpret_cast<const uint32_t*>(vals));
+                } else if (a.k_out == 4) {
+                    ko_dims = __ldg(reinterpret_cast<const uint32_t*>(a.ko_idx + rec));
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(vals));
+                    ko_v01 = v.x; ko_v23 = v.y;
+                } else if (a.k_out == 1) {
+                    ko_dims = __ldg(a.ko_idx + rec);
+                    ko_v01 = __ldg(vals);
+                } else {
+                    ko_dims = (uint32_t)__ldg(a.ko_idx + rec) | ((uint32_t)__ldg(a.ko_idx + rec + 1) << 8) | ((uint32_t)__ldg(a.ko_idx + rec + 2) << 16);
+                    ko_v01 = (uint32_t)__ldg(vals) | ((uint32_t)__ldg(vals + 1) << 16);
+                    ko_v23 = __ldg(vals + 2);
+                }
+            }
+        };
+        ko_fetch(warp);
+
         for (int tile = warp; tile < n_tiles; tile += kWarps) {
             cp_async_wait<1>();          // pending [K(i), V(i)] -> K(i) landed
             __syncwarp();
             const int tok = t0 + tile * kTile + lane;
             const bool valid = tok < t1;
+            const uint32_t my_dims = ko_dims, my_v01 = ko_v01, my_v23 = ko_v23;
+            ko_fetch(tile + kWarps);
 
             // ------------------------------------------------ QK: 32 conflict-free LUT gathers for my token
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -219,6 +256,29 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                     else fhadd2(s4[0], s4[1], e.x);
                     if constexpr (G == 4) fhadd2(s4[2], s4[3], e.y);
                 }
+            }
+            if constexpr (OUT) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < a.k_out) {
+                        const uint32_t pair = i < 2 ? my_v01 : my_v23;
+                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : (pair & 0xffffu));
+                        const float dv = valid ? io<T>::to_f(*reinterpret_cast<const T*>(&hv)) : 0.f;
+                        // q_g[dim] for the G heads from the [dim][head] table in shared memory (one load)
+                        const int dim = (my_dims >> (8 * i)) & 0xff;
+                        const unsigned char* qrow = smem + kMiscOff + dim * (2 * G);
+                        if constexpr (G == 4) {
+                            const uint2 w = *reinterpret_cast<const uint2*>(qrow);
+                            const float2 q01 = io<T>::to_f2(w.x), q23 = io<T>::to_f2(w.y);
+                            s4[0] = fmaf(q01.x, dv, s4[0]); s4[1] = fmaf(q01.y, dv, s4[1]);
+                            s4[2] = fmaf(q23.x, dv, s4[2]); s4[3] = fmaf(q23.y, dv, s4[3]);
+                        } else if constexpr (G == 2) {
+                            const float2 q01 = io<T>::to_f2(*reinterpret_cast<const uint32_t*>(qrow));
+                            s4[0] = fmaf(q01.x, dv, s4[0]); s4[1] = fmaf(q01.y, dv, s4[1]);
+                        } else {
+                            s4[0] = fmaf(io<T>::to_f(*reinterpret_cast<const T*>(qrow)), dv, s4[0]);
+                        }
+                    }
             }
             __syncwarp();
             issue(tile + kWarps, kbase, ks_s);
@@ -390,12 +450,12 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
     if (last) merge_group<T>(a, b, hk, np, xch);
 }
 
-template <typename T, int G>
+template <typename T, int G, int OUT>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_dm4_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
     if (!a.flat) {
         int t0, t1;
         split_range(a, blockIdx.x, t0, t1);
-        attn_dm4_segment<T, G>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits);
+        attn_dm4_segment<T, G, OUT>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits);
         return;
     }
     // flat scheduling: see attn_fast_kernel (attn_fast.cu)
@@ -410,25 +470,25 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_dm4_kernel(const 
         const int first = (int)(real0 / per), last = (int)((real1 - 1) / per);
         const int us = (int)(s0 - real0), ue = (int)(s1 - real0);
         const int t1 = (ue * 64 < a.nk) ? ue * 64 : a.nk;
-        attn_dm4_segment<T, G>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1);
+        attn_dm4_segment<T, G, OUT>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1);
         __syncthreads();
     }
 }
 
-template <typename T, int G>
+template <typename T, int G, int OUT>
 static int launch_dm4_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
-    const size_t smem = dm4::kLutBytes + kVtabBytes + 32768 + 3072 + kWarps * kTile * 8 + 256;
+    const size_t smem = dm4::kLutBytes + kVtabBytes + 32768 + 3072 + kWarps * kTile * 8 + (OUT ? 1024 : 256);
     static_assert(32768 + 3072 >= 2 * kWarps * 4 * 130 * sizeof(float) + 64, "stage area too small for the combine");
     static_assert(32768 + 3072 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static bool configured = false;
     if (!configured) {
-        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_dm4_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_dm4_kernel<T, G, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
     if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
-    attn_fast_dm4_kernel<T, G><<<grid, block, smem, stream>>>(a, prepared, gsub);
+    attn_fast_dm4_kernel<T, G, OUT><<<grid, block, smem, stream>>>(a, prepared, gsub);
     MILLION_CUDA_OK(cudaGetLastError());
     return MILLION_OK;
 }
@@ -436,13 +496,13 @@ static int launch_dm4_t(const AttnArgs& a, const uint32_t* prepared, int gsub, c
 int launch_attn_fast_dm4(const AttnArgs& a, int io_dtype, int G, int gsub, const void* prepared, cudaStream_t stream) {
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
     if (io_dtype == MILLION_F16) {
-        if (G == 4) return launch_dm4_t<__half, 4>(a, prep, gsub, stream);
-        if (G == 2) return launch_dm4_t<__half, 2>(a, prep, gsub, stream);
-        return launch_dm4_t<__half, 1>(a, prep, gsub, stream);
+        if (G == 4) return (a.k_out ? launch_dm4_t<__half, 4, 1>(a, prep, gsub, stream) : launch_dm4_t<__half, 4, 0>(a, prep, gsub, stream));
+        if (G == 2) return (a.k_out ? launch_dm4_t<__half, 2, 1>(a, prep, gsub, stream) : launch_dm4_t<__half, 2, 0>(a, prep, gsub, stream));
+        return (a.k_out ? launch_dm4_t<__half, 1, 1>(a, prep, gsub, stream) : launch_dm4_t<__half, 1, 0>(a, prep, gsub, stream));
     }
-    if (G == 4) return launch_dm4_t<__nv_bfloat16, 4>(a, prep, gsub, stream);
-    if (G == 2) return launch_dm4_t<__nv_bfloat16, 2>(a, prep, gsub, stream);
-    return launch_dm4_t<__nv_bfloat16, 1>(a, prep, gsub, stream);
+    if (G == 4) return (a.k_out ? launch_dm4_t<__nv_bfloat16, 4, 1>(a, prep, gsub, stream) : launch_dm4_t<__nv_bfloat16, 4, 0>(a, prep, gsub, stream));
+    if (G == 2) return (a.k_out ? launch_dm4_t<__nv_bfloat16, 2, 1>(a, prep, gsub, stream) : launch_dm4_t<__nv_bfloat16, 2, 0>(a, prep, gsub, stream));
+    return (a.k_out ? launch_dm4_t<__nv_bfloat16, 1, 1>(a, prep, gsub, stream) : launch_dm4_t<__nv_bfloat16, 1, 0>(a, prep, gsub, stream));
 }
 
 }  // namespace million

@@ -67,10 +67,10 @@ def test_reconstruct_with_outliers(M):
     assert np.abs(got - X.float().numpy()).max() < 0.25 * np.abs(plain - X.float().numpy()).max()
 
 
-def _attn_case(M, bs, nh, nh_k, nk, r, k_out, v_out, impl, dtype=torch.float16, seed=11):
+def _attn_case(M, bs, nh, nh_k, nk, r, k_out, v_out, impl, dtype=torch.float16, seed=11, Mm=64):
     rng = np.random.default_rng(seed)
-    K, cent = _data(seed, bs, nh_k, nk, dtype=dtype)
-    V, vcent = _data(seed + 1, bs, nh_k, nk, heavy=False, dtype=dtype)
+    K, cent = _data(seed, bs, nh_k, nk, Mm=Mm, dtype=dtype)
+    V, vcent = _data(seed + 1, bs, nh_k, nk, Mm=Mm, heavy=False, dtype=dtype)
     q = torch.from_numpy(rng.standard_normal((bs, nh, 1, 128), dtype=np.float32)).to(dtype)
     kres = torch.from_numpy(rng.standard_normal((bs, nh_k, 128, 128), dtype=np.float32)).to(dtype)
     vres = torch.from_numpy(rng.standard_normal((bs, nh_k, 128, 128), dtype=np.float32)).to(dtype)
@@ -106,6 +106,14 @@ def test_attn_fast_k_outliers(M, dtype, k_out, nh, nh_k, nk):
     from million_b200 import _lib as L
     got, ref = _attn_case(M, 2, nh, nh_k, nk, 128, k_out, 0, L.IMPL_FAST, dtype=dtype)
     np.testing.assert_allclose(got, ref, atol=ATOL if dtype == torch.float16 else 8e-3, rtol=RTOL)
+
+
+@pytest.mark.parametrize("nh,nh_k,nk,k_out", [(8, 2, 1500, 2), (4, 4, 777, 1), (4, 2, 2100, 4)])
+def test_attn_fast_k_outliers_m32(M, nh, nh_k, nk, k_out):
+    """M = 32 (d_m = 4, the reference's "2-bit"): attn_fast_dm4.cu"""
+    from million_b200 import _lib as L
+    got, ref = _attn_case(M, 2, nh, nh_k, nk, 100, k_out, 0, L.IMPL_FAST, Mm=32)
+    np.testing.assert_allclose(got, ref, atol=ATOL, rtol=RTOL)
 
 
 def test_attn_fast_k_outliers_long_batch(M):
