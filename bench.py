@@ -164,14 +164,19 @@ def build_layers(torch, bs, nk, device, n_layers):
     return kcent, vcent, layers
 
 
-def time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=0):
-    """Graph-replayed 32-layer step, inputs resident.  Returns (seconds for `steps` steps, launches)."""
+def time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=0, k_out=0):
+    """Graph-replayed 32-layer step, inputs resident.  Returns (seconds for `steps` steps, launches).
+    k_out > 0: with a K-side outlier store of that many (dim, delta) records per coded token (extension)."""
     kcent, vcent, layers = build_layers(torch, bs, nk, device, LAYERS)
     ws = ops.attn_workspace(device, bs, NH, NH_K, D, ops.default_splits(bs, NH_K, nk))
+    for L_ in layers:
+        L_["ko"] = (torch.randint(0, D, (bs, NH_K, nk, k_out), dtype=torch.uint8, device=device),
+                    torch.randn(bs, NH_K, nk, k_out, device=device).half()) if k_out else None
 
     def step():
         for L_ in layers:
-            ops.pq_decode_attn(L_["q"], L_["kc"], L_["vc"], kcent, vcent, L_["kres"], L_["vres"], r, out=L_["out"], workspace=ws, impl=impl)
+            ops.pq_decode_attn(L_["q"], L_["kc"], L_["vc"], kcent, vcent, L_["kres"], L_["vres"], r, out=L_["out"], workspace=ws, impl=impl,
+                               k_outliers=L_["ko"])
 
     s = torch.cuda.Stream(device=device)
     s.wait_stream(torch.cuda.current_stream())
@@ -292,6 +297,17 @@ def main():
         a1 = algorithmic_bytes(1, nk, r) / (s1 / launches) / 1e9
         extra["bs1"] = {"tokens_per_s": steps / s1, "us_per_layer": s1 / launches * 1e6, "achieved_GBps": a1, "frac": a1 / peak}
         del g1, l1, c1
+        # the same step with a K-side outlier store (2 records per coded token and KV head: +6 bytes on 128)
+        g2, l2, c2 = time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=args.kernel, k_out=2)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(steps):
+            g2.replay()
+        e1.record(); torch.cuda.synchronize()
+        s2 = e0.elapsed_time(e1) / 1e3
+        alg2 = alg + 3 * 2 * bs * NH_K * nk
+        extra["k_outliers_2"] = {"tokens_per_s": bs * steps / s2, "us_per_layer": s2 / launches * 1e6,
+                                 "achieved_GBps": alg2 / (s2 / launches) / 1e9, "frac": alg2 / (s2 / launches) / 1e9 / peak}
+        del g2, l2, c2
         try:
             extra["encode"] = encode_rate(torch, ops, device)
         except Exception as e:
