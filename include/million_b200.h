@@ -64,7 +64,9 @@ enum million_v_layout {
 enum million_impl {
     MILLION_IMPL_AUTO = 0,
     MILLION_IMPL_GENERIC = 1, /* plain SIMT kernels, every shape */
-    MILLION_IMPL_FAST = 2     /* decode: conflict-free shared-memory LUT gathers (attn_fast.cu); encode: tcgen05 distances */
+    MILLION_IMPL_FAST = 2,    /* decode: conflict-free shared-memory LUT gathers (attn_fast.cu); encode: tcgen05 distances */
+    MILLION_IMPL_GRID = 3     /* encode only, d/M = 2: exact candidate-grid search (encode_grid.cu); `prepared_encoder` must then
+                                 point at the tables of million_pq_encoder_grid_prepare */
 };
 
 int million_abi_version(void);
@@ -91,6 +93,13 @@ int million_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * the exact CUDA-core encoder runs. */
 int64_t million_pq_encoder_prepared_bytes(int d, int M, int C);
 int million_pq_encoder_prepare(const float* cent, int x_dtype, int d, int M, int C, void* prepared, million_stream_t stream);
+
+/* Tables of the candidate-grid encoder (two-dimensional sub-spaces, d = 2M, C <= 256): per sub-space a 64 x 64 grid over the
+ * centroids with, per cell, every centroid that can be nearest to a point of the cell.  Exact: codes are bit-identical to the
+ * brute-force arg-min.  Asynchronous on `stream`, no host synchronisation; 0 bytes / MILLION_ERR_UNSUPPORTED for other shapes.
+ * Pass the buffer as `prepared_encoder` together with impl = MILLION_IMPL_GRID. */
+int64_t million_pq_encoder_grid_prepared_bytes(int d, int M, int C);
+int million_pq_encoder_grid_prepare(const float* cent, int d, int M, int C, void* prepared, million_stream_t stream);
 
 int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride,
                       const float* cent, const void* prepared_encoder /* may be NULL */,

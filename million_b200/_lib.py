@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("MILLION_B200_LIB") or os.path.join(HERE, "libmillion_
 MILLION_F16, MILLION_BF16, MILLION_F32 = 0, 1, 2
 MILLION_OK, MILLION_ERR_INVALID, MILLION_ERR_UNSUPPORTED, MILLION_ERR_CUDA = 0, 1, 2, 3
 V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
-IMPL_AUTO, IMPL_GENERIC, IMPL_FAST = 0, 1, 2
+IMPL_AUTO, IMPL_GENERIC, IMPL_FAST, IMPL_GRID = 0, 1, 2, 3
 ATTN_PARTIAL_ONLY = 1
 ABI_VERSION = 5
 
@@ -50,6 +50,8 @@ SIGNATURES = {
     "million_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
     "million_pq_encoder_prepared_bytes": (c_i64, [ctypes.c_int] * 3),
     "million_pq_encoder_prepare": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "million_pq_encoder_grid_prepared_bytes": (c_i64, [ctypes.c_int] * 3),
+    "million_pq_encoder_grid_prepare": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "million_pq_encode": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, ctypes.c_int, c_i64, c_i64, c_i64, c_i64,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "million_pq_encode_paged": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_i64,

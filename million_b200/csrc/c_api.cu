@@ -51,12 +51,21 @@ int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C
 int launch_encode_tc(const void* x, int x_dtype, int64_t xhs, const float* cent, const void* prepared, const CodeDst& dst,
                      int n_heads, int n_tokens, int d, int M, int C, cudaStream_t stream, bool probe_only);
 
+int64_t encode_grid_prepared_bytes(int d, int M, int C);
+int launch_encode_grid_prepare(const float* cent, int d, int M, int C, void* out, cudaStream_t stream);
+int launch_encode_grid(const void* x, int x_dtype, int64_t xhs, const float* cent, const void* prepared, const CodeDst& dst, int n_heads,
+                       int n_tokens, int d, int M, int C, cudaStream_t stream, bool probe_only);
+
 static int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float* cent, const void* prepared, void* codes, int code_bytes,
                            int64_t chs, int64_t cts, int64_t cms, int64_t t0, const int64_t* page_ids, int64_t pihs, int page_size,
                            int n_heads, int n_tokens, int d, int M, int C, int impl, cudaStream_t stream) {
     CodeDst dst{codes, code_bytes, chs, cts, cms, t0, page_ids, pihs, page_size, M};
     if (impl == MILLION_IMPL_GENERIC) return launch_encode_generic(x, x_dtype, xhs, cent, dst, n_heads, n_tokens, d, M, C, stream);
     if (impl == MILLION_IMPL_FAST) return launch_encode_tc(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, false);
+    if (impl == MILLION_IMPL_GRID) {
+        if (code_bytes != 1) MILLION_UNSUPPORTED("grid encoder writes one-byte codes");
+        return launch_encode_grid(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, false);
+    }
     // AUTO: the tensor-core encoder pays off from a few hundred vectors on
     if ((int64_t)n_heads * n_tokens >= 256 &&
         launch_encode_tc(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, true) == MILLION_OK)
@@ -93,6 +102,13 @@ int64_t million_pq_encoder_prepared_bytes(int d, int M, int C) { return encode_t
 int million_pq_encoder_prepare(const float* cent, int x_dtype, int d, int M, int C, void* prepared, million_stream_t stream) {
     MILLION_REQUIRE(cent && prepared, "encoder_prepare: null pointer");
     return launch_encode_tc_prepare(cent, x_dtype, d, M, C, prepared, (cudaStream_t)stream);
+}
+
+int64_t million_pq_encoder_grid_prepared_bytes(int d, int M, int C) { return encode_grid_prepared_bytes(d, M, C); }
+
+int million_pq_encoder_grid_prepare(const float* cent, int d, int M, int C, void* prepared, million_stream_t stream) {
+    MILLION_REQUIRE(cent && prepared, "encoder_grid_prepare: null pointer");
+    return launch_encode_grid_prepare(cent, d, M, C, prepared, (cudaStream_t)stream);
 }
 
 int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride, const float* cent, const void* prepared, void* codes, int code_bytes,

@@ -68,6 +68,43 @@ def prepare_encoder(cent_f32, x_dtype):
     return _enc_prepared[key][0]
 
 
+_grid_prepared = {}
+
+
+def prepare_encoder_grid(cent_f32):
+    """Candidate-grid tables of the exact 2-D encoder (d/M = 2, C <= 256), or None for other shapes.  One asynchronous launch per
+    codebook (tensor + version), cached."""
+    M, C, dm = cent_f32.shape
+    nbytes = L.lib().million_pq_encoder_grid_prepared_bytes(M * dm, M, C)
+    if nbytes == 0:
+        return None
+    key = (cent_f32.data_ptr(), cent_f32._version, cent_f32.device)
+    hit = _grid_prepared.get(key)
+    if hit is None:
+        if len(_grid_prepared) > 64:
+            _grid_prepared.clear()
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=cent_f32.device)
+        L.check(L.lib().million_pq_encoder_grid_prepare(_ptr(cent_f32), M * dm, M, C, _ptr(buf), _stream(cent_f32)))
+        hit = (buf, cent_f32)
+        _grid_prepared[key] = hit
+    return hit[0]
+
+
+def _encoder_choice(X, cent_f32, impl, code_bytes):
+    """(impl, prepared) for one encode call: AUTO takes the candidate-grid encoder where it applies (two-dimensional
+    sub-spaces), else the tensor-core encoder, else the generic one (decided inside the library)."""
+    if code_bytes == 1 and impl in (L.IMPL_AUTO, L.IMPL_GRID):
+        grid = prepare_encoder_grid(cent_f32)
+        if grid is not None:
+            eb = X.element_size()
+            if X.data_ptr() % (4 * eb) == 0:
+                return L.IMPL_GRID, grid
+        if impl == L.IMPL_GRID:
+            raise L.MillionError(L.MILLION_ERR_UNSUPPORTED, "grid encoder: shape or alignment not covered")
+    prep = prepare_encoder(cent_f32, X.dtype) if impl != L.IMPL_GENERIC and code_bytes == 1 else None
+    return impl, prep
+
+
 def pq_encode_into(X, cent_f32, codes, *, t0=0, layout="rowmajor", impl=L.IMPL_AUTO):
     """Encode X (bs, nh_k, n, d) and write the codes at token offset t0 of a preallocated cache.
     layout 'rowmajor': codes (bs, nh_k, cap, M); 'transposed': codes (bs, nh_k, M, cap)."""
@@ -84,7 +121,7 @@ def pq_encode_into(X, cent_f32, codes, *, t0=0, layout="rowmajor", impl=L.IMPL_A
         assert codes.shape[0] == bs and codes.shape[1] == nh and codes.shape[2] == M and codes.stride(3) == 1
         hs, ts, ms = codes.stride(1), 1, codes.stride(2)
         assert bs == 1 or codes.stride(0) == nh * codes.stride(1)
-    prep = prepare_encoder(cent_f32, X.dtype) if impl != L.IMPL_GENERIC and codes.element_size() == 1 else None
+    impl, prep = _encoder_choice(X, cent_f32, impl, codes.element_size())
     L.check(L.lib().million_pq_encode(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(prep), _ptr(codes), codes.element_size(),
                                       hs, ts, ms, t0, bs * nh, n, d, M, C, impl, _stream(X)))
     return codes
@@ -110,7 +147,7 @@ def pq_encode_paged(X, cent_f32, page_pool, page_ids, *, t0, impl=L.IMPL_AUTO):
     assert page_pool.dtype == torch.uint8 and page_pool.is_contiguous() and page_pool.shape[1] == M
     assert page_ids.dtype == torch.int64 and page_ids.is_contiguous() and page_ids.shape[:2] == (bs, nh)
     X, xhs = _x_view(X)
-    prep = prepare_encoder(cent_f32, X.dtype) if impl != L.IMPL_GENERIC else None
+    impl, prep = _encoder_choice(X, cent_f32, impl, 1)
     L.check(L.lib().million_pq_encode_paged(_ptr(X), _dt(X), xhs, _ptr(cent_f32), _ptr(prep), _ptr(page_pool), _ptr(page_ids),
                                             page_ids.shape[2], page_pool.shape[2], t0, bs * nh, n, d, M, C, impl, _stream(X)))
 

@@ -60,6 +60,33 @@ def test_encode_random_bit_exact(M, dtype, d, Mm, C):
     assert np.array_equal(got.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_encode_grid_bit_exact(M, dtype, golden):
+    """candidate-grid encoder (d/M = 2): random, heavy-tailed, degenerate codebooks, non-finite inputs; golden vectors"""
+    from million_b200 import _lib as L
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((2, 3, 1501, 128), dtype=np.float32)
+    X *= np.where(rng.random(X.shape) < 0.02, 25.0, 1.0).astype(np.float32)
+    X[0, 0, :50] = np.nan; X[0, 0, 50:60] = np.inf; X[0, 0, 60:70] = 0.0
+    X = torch.from_numpy(X).to(dtype)
+    cent = torch.from_numpy(rng.standard_normal((64, 256, 2), dtype=np.float32)).half().float()
+    cent[1, 100] = cent[1, 7]                                  # duplicate centroid: first index must win
+    cent[2] = cent[2] * 0.01 + 1.0                             # tight cluster (cells overflow -> full scan)
+    cent[3, :, 1] = 0.0                                        # collinear
+    cent[4] = cent[4, 0]                                       # all identical
+    X[1, 1, :256] = cent.permute(1, 0, 2).reshape(256, 128).to(dtype)     # points exactly on centroids
+    with np.errstate(invalid="ignore"):
+        ref = O.pq_encode(X.float().numpy(), cent.numpy())
+    got = M.pq_encode(X.cuda(), cent.cuda(), impl=L.IMPL_GRID)
+    assert np.array_equal(got.cpu().numpy(), ref)
+    assert np.array_equal(M.pq_encode(X.cuda(), cent.cuda()).cpu().numpy(), ref)     # AUTO takes the same path
+    for i in range(5):
+        Xg, cg = golden[f"enc{i}_X"], golden[f"enc{i}_cent"]
+        if cg.shape[2] == 2 and cg.shape[1] <= 256 and dtype == torch.float16:
+            g = M.pq_encode(dev(Xg), dev(cg, torch.float32), impl=L.IMPL_GRID)
+            assert np.array_equal(g.cpu().numpy(), golden[f"enc{i}_codes_keops"])
+
+
 def test_encode_ties_and_wide_codes(M, golden):
     got = M.pq_encode(dev(golden["tie_X"]), dev(golden["tie_cent"], torch.float32))
     assert np.array_equal(got.cpu().numpy(), golden["tie_codes"])
