@@ -193,22 +193,28 @@ def time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=0, k_out=0)
 
 
 def encode_rate(torch, ops, device):
-    """PQ encode throughput on Llama-3.1-8B prefill shapes: K of one layer = 8 kv-heads x 32768 tokens (tcgen05 encoder)."""
+    """PQ encode throughput on Llama-3.1-8B prefill shapes: K of one layer = 8 kv-heads x 32768 tokens, for the encoder AUTO
+    picks (the exact candidate-grid encoder for d/M = 2) and for the tcgen05 distance encoder."""
+    from million_b200 import _lib as L
     n = 32768
     X = torch.randn(1, NH_K, n, D, device=device).half()
     cent = torch.randn(M, C, D // M, device=device).half().float().contiguous()
     codes = torch.empty(1, NH_K, n, M, dtype=torch.uint8, device=device)
-    for _ in range(3):
-        ops.pq_encode_into(X, cent, codes)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(10):
-        ops.pq_encode_into(X, cent, codes)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    vec_per_s = NH_K * n / (ms * 1e-3)
-    return {"M_head_vectors_per_s": vec_per_s / 1e6, "Mtok_per_s_32_layers_K_and_V": vec_per_s / (2 * NH_K * LAYERS) / 1e6,
-            "algorithmic_TFLOPs": vec_per_s * 2 * D * C / 1e12, "ms_per_layer_K_32k": ms}
+    out = {}
+    for name, impl in (("auto_grid", L.IMPL_AUTO), ("tcgen05", L.IMPL_FAST)):
+        for _ in range(3):
+            ops.pq_encode_into(X, cent, codes, impl=impl)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(10):
+            ops.pq_encode_into(X, cent, codes, impl=impl)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        vec_per_s = NH_K * n / (ms * 1e-3)
+        out[name] = {"M_head_vectors_per_s": vec_per_s / 1e6, "Mtok_per_s_32_layers_K_and_V": vec_per_s / (2 * NH_K * LAYERS) / 1e6,
+                     "brute_force_equivalent_TFLOPs": vec_per_s * 2 * D * C / 1e12, "ms_per_layer_K_32k": ms,
+                     "hbm_GBps_input_plus_codes": vec_per_s * (2 * D + M) / 1e9}
+    return out
 
 
 def ncu_traffic(bs):
