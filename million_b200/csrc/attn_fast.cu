@@ -605,7 +605,8 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
     // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
     const bool last = last_cta_of_group(a.counters, hb, np * gsub, flag);
     dbg_stamp(a, 5, piece);
-    if (last) merge_group<T>(a, b, hk, np, xch, reinterpret_cast<float*>(lut_p), LutCfg<G>::bytes / 4,
+    if (last) merge_group<T>(a, b, hk, np, xch, reinterpret_cast<float*>(lut_p), (LutCfg<G>::bytes + kVtabBytes) / 4,   // LUT + V table: both dead, adjacent
+                            
                              reinterpret_cast<unsigned long long*>(smem + kMiscOff + 160), piece);   // the K LUT is dead by now
     dbg_stamp(a, 6, piece);
 }

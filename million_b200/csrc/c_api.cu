@@ -193,7 +193,7 @@ int million_pq_decode_attn_default_splits(int bs, int nh_k, int nk) {
     // build once per CTA.  Never fewer than 128 coded tokens per split.
     int max_s = (nk + 127) / 128;
     if (max_s < 1) max_s = 1;
-    if (max_s > 64) max_s = 64;
+    if (max_s > 192) max_s = 192;   // one group on 148 SMs (KV-head sharding at batch 1) wants one split per SM
     int best_s = 1;
     double best_cost = 1e30;
     for (int s = 1; s <= max_s; ++s) {
