@@ -131,13 +131,13 @@ class PagedPQCache(DynamicPQCache):
 
     def __init__(self, *, bs, nh, num_key_value_heads, M, layer_num, dtype=torch.uint8, nbits=8, d=128,
                  scalar_t=torch.float32, page_size=64, extended_residual_size=128, max_pages_per_layer=None,
-                 async_flush=True, device='cuda'):
+                 async_flush=True, device='cuda', outliers=(0, 0)):
         self.page_size = page_size
         self.extended_residual_size = extended_residual_size
         self.max_pages_per_layer = max_pages_per_layer
         self._stats = {'flushes': 0, 'paged_kernel_calls': 0, 'prefill_tokens': 0}
         super().__init__(bs=bs, nh=nh, num_key_value_heads=num_key_value_heads, M=M, layer_num=layer_num, dtype=dtype,
-                         nbits=nbits, d=d, scalar_t=scalar_t, async_flush=async_flush, device=device)
+                         nbits=nbits, d=d, scalar_t=scalar_t, async_flush=async_flush, device=device, outliers=outliers)
 
     def init_cache(self):
         """paged_pq_utils.py:68-128."""
@@ -190,6 +190,36 @@ class PagedPQCache(DynamicPQCache):
         tab[:, :, n_old:n_old + n_new_chunks] = new.to(self.device)
         self._n_pages[layer_idx] = n_old + n_new_chunks
 
+    def _reserve_k(self, layer_idx, n):
+        ks = self._k[layer_idx]
+        ks.reserve(ks.len + n)
+        if self._ko[layer_idx] is not None:
+            self._ko[layer_idx].reserve(ks.cap, ks.len)
+        if self._vo[layer_idx] is not None:       # V records are indexed by token like K's, whatever page the codes live in
+            self._vo[layer_idx].reserve(ks.cap, self._v_tokens[layer_idx])
+
+    def _encode_k(self, key_states, layer_idx):
+        ks, ko = self._k[layer_idx], self._ko[layer_idx]
+        if ko is not None:
+            key_states = ops.outlier_split_into(key_states, self._key_cent_f32, ko.idx, ko.val, t0=ks.len)
+        ops.pq_encode_into(key_states, self._key_cent_f32, ks.buf, t0=ks.len)
+
+    def _encode_v(self, value_states, layer_idx):
+        vo = self._vo[layer_idx]
+        if vo is not None:
+            value_states = ops.outlier_split_into(value_states, self._value_cent_f32, vo.idx, vo.val, t0=self._v_tokens[layer_idx])
+        ops.pq_encode_paged(value_states, self._value_cent_f32, self.page_managers[layer_idx].page_pool,
+                            self._table[layer_idx], t0=self._v_tokens[layer_idx])
+
+    def _reconstruct_v(self, layer_idx, n_last=None, dtype=None):
+        T = self._v_tokens[layer_idx]
+        n = T if n_last is None else n_last
+        vt = self.value_cache[layer_idx][..., T - n:].transpose(2, 3)
+        x = sa_decode_4d(vt, self.value_cent if dtype is None else self.value_cent.to(dtype))
+        if self._vo[layer_idx] is not None and n:
+            ops.outlier_apply(x, self._vo[layer_idx].idx, self._vo[layer_idx].val, t0=T - n)
+        return x
+
     def _encode_append(self, key_states, value_states, layer_idx, count_seen=True):
         """K codes row-major in place; V codes into pages through the block table.  Requires the V token count to
         be page aligned before the append (true for prefill-from-empty and for page-sized flushes)."""
@@ -197,8 +227,8 @@ class PagedPQCache(DynamicPQCache):
             self._finish_async_flush(layer_idx)
         n = key_states.size(2)
         ks = self._k[layer_idx]
-        ks.reserve(ks.len + n)
-        ops.pq_encode_into(key_states, self._key_cent_f32, ks.buf, t0=ks.len)
+        self._reserve_k(layer_idx, n)
+        self._encode_k(key_states, layer_idx)
         self._encode_v_pages(value_states, layer_idx, n)
         ks.len += n
         self._v_tokens[layer_idx] += n
@@ -214,8 +244,7 @@ class PagedPQCache(DynamicPQCache):
 
     def _encode_v_pages(self, value_states, layer_idx, n):
         self._reserve_pages(layer_idx, n)
-        ops.pq_encode_paged(value_states, self._value_cent_f32, self.page_managers[layer_idx].page_pool,
-                            self._table[layer_idx], t0=self._v_tokens[layer_idx])
+        self._encode_v(value_states, layer_idx)
 
     def cat_codes(self, key_codes, value_codes, layer_idx):
         raise NotImplementedError("PagedPQCache stores V in pages; use prefill/update/decoding_with_pages")
@@ -225,11 +254,10 @@ class PagedPQCache(DynamicPQCache):
         past = self._k[layer_idx].len
         if distort_recent:
             self._encode_append(key_states, value_states, layer_idx)
-            return (sa_decode_4d(self.key_cache[layer_idx], self.key_cent),
-                    sa_decode_4d(self.value_cache[layer_idx].transpose(2, 3), self.value_cent))
+            return self._reconstruct(layer_idx, 'k'), self._reconstruct_v(layer_idx)
         if past > 0:
-            pk = sa_decode_4d(self.key_cache[layer_idx], self.key_cent)
-            pv = sa_decode_4d(self.value_cache[layer_idx].transpose(2, 3), self.value_cent)
+            pk = self._reconstruct(layer_idx, 'k')
+            pv = self._reconstruct_v(layer_idx)
         self._encode_append(key_states, value_states, layer_idx)
         if past > 0:
             key_states = torch.cat([pk.to(key_states.dtype), key_states], dim=2)
@@ -243,10 +271,8 @@ class PagedPQCache(DynamicPQCache):
         self._stats['prefill_tokens'] += n
         self._encode_append(key_states, value_states, layer_idx)
         if distort_recent is True:
-            ks = self._k[layer_idx]
-            key_states = sa_decode_4d(ks.view()[:, :, ks.len - n:], self.key_cent.to(key_states.dtype))
-            vt = self.value_cache[layer_idx][..., self._v_tokens[layer_idx] - n:].transpose(2, 3)
-            value_states = sa_decode_4d(vt, self.value_cent.to(value_states.dtype))
+            key_states = self._reconstruct(layer_idx, 'k', n, key_states.dtype)
+            value_states = self._reconstruct_v(layer_idx, n, value_states.dtype)
         return self._prefill_attention(query_states, key_states, value_states)
 
     # ---- flush (paged_pq_utils.py:130-210)
@@ -270,16 +296,14 @@ class PagedPQCache(DynamicPQCache):
         self._stats['flushes'] += 1
 
     def _start_async_flush(self, layer_idx, n):
-        ks = self._k[layer_idx]
-        ks.reserve(ks.len + n)
+        self._reserve_k(layer_idx, n)
         self._reserve_pages(layer_idx, n)
         main = torch.cuda.current_stream(self.device)
         side = self._side_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            ops.pq_encode_into(self.key_residual_cache[layer_idx][:, :, :n], self._key_cent_f32, ks.buf, t0=ks.len)
-            ops.pq_encode_paged(self.value_residual_cache[layer_idx][:, :, :n], self._value_cent_f32,
-                                self.page_managers[layer_idx].page_pool, self._table[layer_idx], t0=self._v_tokens[layer_idx])
+            self._encode_k(self.key_residual_cache[layer_idx][:, :, :n], layer_idx)
+            self._encode_v(self.value_residual_cache[layer_idx][:, :, :n], layer_idx)
             ev = torch.cuda.Event()
             ev.record(side)
         self._pending[layer_idx] = (ev, n)
@@ -322,6 +346,16 @@ class PagedPQCache(DynamicPQCache):
     def _call_paged_kernel(self, query_states, layer_idx, residual_length):
         """paged_pq_utils.py:399-681 — the 13-argument paged kernel call, for every (b, h) (the reference builds
         its pool from batch 0 / head 0 only, Appendix B.3)."""
+        if self.k_out or self.v_out:
+            # the reference's 13-argument paged call (paged_pq_utils.py:621-635) has no place for the side store
+            ks = self._k[layer_idx]
+            kc, vc = self._attn_cents(query_states.dtype)
+            self._stats['paged_kernel_calls'] += 1
+            return ops.pq_decode_attn(query_states, ks.view(), self.page_managers[layer_idx].page_pool, kc, vc,
+                                      self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], residual_length,
+                                      v_layout=L.V_PAGED, v_page_ids=self._table[layer_idx], page_size=self.page_size,
+                                      k_outliers=self._ko[layer_idx].view(ks.len) if self.k_out else None,
+                                      v_outliers=self._vo[layer_idx].view(ks.len) if self.v_out else None)
         Ns = l2Ns(self.seen_tokens[layer_idx])
         name = f"flash_decoding_paged_v_{'bf16' if query_states.dtype == torch.bfloat16 else 'f16'}u8_Ns{Ns}Lt{self.extended_residual_size}d{self.d}M{self.M}C256"
         from . import bindings

@@ -187,3 +187,72 @@ def test_cache_with_outliers_prefill_decode(M):
         outs[async_flush] = torch.stack(steps)
     assert torch.equal(outs[True], outs[False])
     Singleton.clear_instance()
+
+
+def test_outlier_store_reduces_attention_error(M):
+    """What the store is for: keys with a few heavy channels (heavy-tailed key channels).  Against EXACT fp32 attention
+    on the unquantized K/V, PQ + 2 K-side records per token must be several times closer than plain PQ with the same codebook."""
+    from million_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    bs, nh, nh_k, nk = 1, 8, 2, 4096
+    K = rng.standard_normal((bs, nh_k, nk, 128), dtype=np.float32)
+    K[..., [11, 90]] *= 10.0                                             # two heavy channels (per-token spread: a common offset would cancel in the softmax)
+    V = rng.standard_normal((bs, nh_k, nk, 128), dtype=np.float32)
+    q = rng.standard_normal((bs, nh, 1, 128), dtype=np.float32)
+    cent = torch.from_numpy(rng.standard_normal((64, 256, 2), dtype=np.float32)).half()
+    Kh, Vh, qh = (torch.from_numpy(a).half().cuda() for a in (K, V, q))
+    zres = torch.zeros(bs, nh_k, 128, 128, dtype=torch.float16, device="cuda")
+    c32, c16 = cent.float().cuda(), cent.cuda()
+    # exact attention on the fp16 inputs
+    G = nh // nh_k
+    Kf, Vf = Kh.float().repeat_interleave(G, 1), Vh.float().repeat_interleave(G, 1)
+    exact = torch.softmax(qh.float() @ Kf.transpose(-1, -2) / 128 ** 0.5, -1) @ Vf
+    vc = M.pq_encode(Vh, c32)
+    plain = M.pq_decode_attn(qh, M.pq_encode(Kh, c32), vc, c16, c16, zres, zres, 0)
+    kc, ki, kv = M.pq_encode_outliers(Kh, c32, 2)
+    withs = M.pq_decode_attn(qh, kc, vc, c16, c16, zres, zres, 0, k_outliers=(ki, kv), impl=L.IMPL_FAST)
+    # V is quantized identically in both runs: compare against exact attention over the SAME quantized V
+    Vq = M.pq_decode(vc, c16).float().repeat_interleave(G, 1)
+    exact_q = torch.softmax(qh.float() @ Kf.transpose(-1, -2) / 128 ** 0.5, -1) @ Vq
+    e_plain = (plain.float() - exact_q).abs().max().item()
+    e_with = (withs.float() - exact_q).abs().max().item()
+    assert (ki.cpu().numpy()[..., :2] == 11).any() and e_with < 0.5 * e_plain, (e_plain, e_with)
+
+
+def test_paged_cache_with_outliers(M):
+    """PagedPQCache(outliers=(2, 1)): K records through the fast paged kernel when only K has them, K + V records through the generic
+    one; prefill + decode across page flushes against the oracle attention on the cache's own state."""
+    from million_b200.paged_pq_utils import PagedPQCache
+    from million_b200.pq_utils import Singleton
+    for outl in ((2, 0), (2, 1)):
+        Singleton.clear_instance()
+        torch.manual_seed(1)
+        bs, nh, nh_k, T = 1, 8, 2, 256
+        cache = PagedPQCache(bs=bs, nh=nh, num_key_value_heads=nh_k, M=64, layer_num=1, scalar_t=torch.float16, outliers=outl)
+        cent = torch.randn(64, 256, 2, device="cuda").half()
+        cache.set_cent(cent, cent)
+        k = torch.randn(bs, nh_k, T, 128, device="cuda").half(); k[..., 7] *= 15
+        v = torch.randn(bs, nh_k, T, 128, device="cuda").half(); v[..., 100] *= 10
+        cache.prefill(torch.randn(bs, nh, T, 128, device="cuda").half(), k, v, 0)
+        codes, idx, val = O.pq_encode_outliers(k.float().cpu().numpy(), cent.float().cpu().numpy(), 2)
+        assert np.array_equal(cache.key_cache[0].cpu().numpy(), codes)
+        f = lambda t: t.float().cpu().numpy()
+        for step in range(200):                 # window 128, flush granularity 64: several page flushes
+            qs = torch.randn(bs, nh, 1, 128, device="cuda").half()
+            kn = torch.randn(bs, nh_k, 1, 128, device="cuda").half(); kn[..., 7] *= 15
+            vn = torch.randn(bs, nh_k, 1, 128, device="cuda").half(); vn[..., 100] *= 10
+            out = cache.decoding_with_pages(qs, kn, vn, 0)
+            if step in (0, 63, 64, 130, 199):
+                torch.cuda.synchronize()
+                n, r = cache._k[0].len, cache.residualed_tokens[0]
+                vcodes = cache.value_cache[0][..., :n].transpose(2, 3).contiguous().cpu().numpy()
+                ki, kv = cache._ko[0].view(n)
+                vout = None
+                if outl[1]:
+                    vi, vv = cache._vo[0].view(n)
+                    vout = (vi.cpu().numpy(), f(vv))
+                ref = O.pq_decode_attn_outliers(f(qs), cache.key_cache[0][:, :, :n].cpu().numpy(), vcodes, f(cent), f(cent),
+                                                f(cache.key_residual_cache[0]), f(cache.value_residual_cache[0]), r,
+                                                kout=(ki.cpu().numpy(), f(kv)), vout=vout)
+                np.testing.assert_allclose(f(out), ref, atol=ATOL, rtol=RTOL)
+    Singleton.clear_instance()
