@@ -20,17 +20,24 @@ struct CodeDst {
         }
         return head * head_stride + (t0 + t) * token_stride + m * m_stride;
     }
-    // codes of the adjacent sub-spaces m (even) and m + 1: one 2-byte store where they are adjacent in memory
+    // codes of the adjacent sub-spaces m (even) and m + 1: one address computation (one block-table lookup), and one 2-byte
+    // store where the two codes are adjacent in memory
     __device__ __forceinline__ void put2(int head, int t, int m, int c0, int c1) const {
-        if (!page_ids && code_bytes == 1 && m_stride == 1) {
-            const int64_t off = offset(head, t, m);
-            if (((reinterpret_cast<uintptr_t>(base) + off) & 1) == 0) {
-                *reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(base) + off) = (uint16_t)(c0 | (c1 << 8));
-                return;
+        const int64_t off = offset(head, t, m);
+        const int64_t step = page_ids ? (int64_t)page_size : m_stride;
+        if (code_bytes == 1) {
+            uint8_t* p = reinterpret_cast<uint8_t*>(base) + off;
+            if (step == 1 && (reinterpret_cast<uintptr_t>(p) & 1) == 0) {
+                *reinterpret_cast<uint16_t*>(p) = (uint16_t)(c0 | (c1 << 8));
+            } else {
+                p[0] = (uint8_t)c0;
+                p[step] = (uint8_t)c1;
             }
+        } else {
+            uint16_t* p = reinterpret_cast<uint16_t*>(base) + off;
+            p[0] = (uint16_t)c0;
+            p[step] = (uint16_t)c1;
         }
-        put(head, t, m, c0);
-        put(head, t, m + 1, c1);
     }
     __device__ __forceinline__ void put(int head, int t, int m, int code) const {
         const int64_t off = offset(head, t, m);

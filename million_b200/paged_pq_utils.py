@@ -92,7 +92,15 @@ class PageManager:
                 raise RuntimeError(f"Cannot bulk-allocate pages: {e}")
         if len(self._free) < n:
             raise RuntimeError(f"Cannot bulk-allocate {n} pages: max_pages={self.max_pages}")
-        return [self.allocate_page() for _ in range(n)]
+        # bulk form of n allocate_page() calls (same order: lowest id first), without n trips through the interpreter
+        ids = self._free[-n:][::-1]
+        del self._free[-n:]
+        self.page_reuse_count += len(self._ever_used.intersection(ids))
+        self._ever_used.update(ids)
+        ap = self.allocated_pages
+        ap.update((pid, {'allocation_count': ap[pid]['allocation_count'] + 1 if pid in ap else 1}) for pid in ids)
+        self.total_allocations += n
+        return ids
 
     def free_page(self, page_id: int):
         if page_id not in self.allocated_pages:
@@ -147,11 +155,27 @@ class PagedPQCache(DynamicPQCache):
         self.page_managers = [PageManager(self.page_size, initial_pages=64, max_pages=self.max_pages_per_layer, M=self.M,
                                           device=self.device) for _ in range(self.layer_num)]
         # block tables: host list-of-lists [layer][b][h] -> page ids, mirrored on the device as (bs, nh_k, cap) int64
-        self.value_page_ids = [[[[] for _ in range(self.num_key_value_heads)] for _ in range(self.bs)] for _ in range(self.layer_num)]
+        self._grow_log = [[] for _ in range(self.layer_num)]    # page ids of every allocation, in allocation order (host mirror)
         self._table = [torch.zeros((self.bs, self.num_key_value_heads, 0), dtype=torch.int64, device=self.device)
                        for _ in range(self.layer_num)]
         self._n_pages = [0 for _ in range(self.layer_num)]
         self._v_tokens = [0 for _ in range(self.layer_num)]
+
+    @property
+    def value_page_ids(self):
+        """[layer][b][h] -> page ids (dynamic_paged_pq_utils.py:453-456), materialised on demand: filling these Python lists
+        eagerly cost ~25 ms of host time per 32K-token prefill (4096 appends per layer)."""
+        out = []
+        for l in range(self.layer_num):
+            per = [[[] for _ in range(self.num_key_value_heads)] for _ in range(self.bs)]
+            for ids in self._grow_log[l]:
+                it = iter(ids)
+                for _ in range(len(ids) // (self.bs * self.num_key_value_heads)):
+                    for b in range(self.bs):
+                        for h in range(self.num_key_value_heads):
+                            per[b][h].append(next(it))
+            out.append(per)
+        return out
 
     # value_cache keeps the live class's (bs, nh_k, M, T) face, materialised from the pages on demand
     @property
@@ -175,11 +199,7 @@ class PagedPQCache(DynamicPQCache):
         else:
             new = torch.tensor(ids, dtype=torch.int64)
         new = new.view(n_new_chunks, self.bs, self.num_key_value_heads).permute(1, 2, 0)
-        it = iter(ids)
-        for _ in range(n_new_chunks):
-            for b in range(self.bs):
-                for h in range(self.num_key_value_heads):
-                    self.value_page_ids[layer_idx][b][h].append(next(it))
+        self._grow_log[layer_idx].append(ids)     # value_page_ids (the reference's list-of-lists view) is built from this on demand
         n_old = self._n_pages[layer_idx]
         tab = self._table[layer_idx]
         if n_old + n_new_chunks > tab.shape[2]:
