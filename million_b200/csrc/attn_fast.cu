@@ -173,7 +173,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         issue_v(warp);
         // K LUT: thread owns column `col` (= one sub-space) and walks the codes.  LUT[c][col] = <q_h[m], Kcent[m][c]> for the
         // G heads of the group: fp32 products of fp16 operands, rounded once to fp16 (G=1 keeps fp32 entries).  The gather table
-        // kT (64 KB, L2 resident) is read straight into registers, 16 coalesced loads in flight per thread (staging it through
+        // kT (64 KB, L2 resident) is read straight into registers, 32 coalesced loads in flight per thread (staging it through
         // shared memory cost four block barriers and kept the stage area busy).
         const int col = tid & 63;
         const int bb = ((col >> 5) << 1) | ((col >> 4) & 1), W = col & 15, m = 4 * W + bb;
@@ -184,7 +184,10 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             q0[g] = io<T>::to_f(q[2 * m]);
             q1[g] = io<T>::to_f(q[2 * m + 1]);
         }
-        constexpr int kRowsPerPass = kThreads / 64, kBatch = 16;
+        #ifndef MILLION_LUT_BATCH
+#define MILLION_LUT_BATCH 32
+#endif
+        constexpr int kRowsPerPass = kThreads / 64, kBatch = MILLION_LUT_BATCH;
 #pragma unroll 1
         for (int c0 = tid >> 6; c0 < 256; c0 += kRowsPerPass * kBatch) {
             uint32_t raw[kBatch];
