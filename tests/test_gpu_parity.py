@@ -319,6 +319,23 @@ def test_full_size_llama31_8b_32k_properties(M):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("bs,nh,nh_k,nk,r", [(1, 32, 8, 5000, 128), (2, 8, 8, 777, 17), (1, 16, 8, 64, 1), (1, 32, 4, 2100, 40), (2, 4, 4, 0, 9)])
+def test_full_size_encode_grid_equals_exact_encoder(M):
+    """BASELINE config 2/3 prefill shape (8 kv-heads x 32768 tokens, M=64): the candidate-grid encoder, the tensor-core encoder and
+    the exact CUDA-core encoder must agree on every one of the 16.8 M codes (the oracle is too slow at this size: the exact
+    encoder is itself pinned to the oracle and the golden vectors by the tests above)."""
+    from million_b200 import _lib as L
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    X = torch.randn(1, 8, 32768, 128, device="cuda", generator=g).half()
+    X *= torch.where(torch.rand(X.shape, device="cuda", generator=g) < 0.01, 20.0, 1.0).half()      # 1 % heavy entries
+    cent = torch.randn(64, 256, 2, device="cuda", generator=g).half().float().contiguous()
+    exact = M.pq_encode(X, cent, impl=L.IMPL_GENERIC)
+    assert torch.equal(M.pq_encode(X, cent, impl=L.IMPL_GRID), exact)
+    assert torch.equal(M.pq_encode(X, cent, impl=L.IMPL_FAST), exact)
+    # idempotence through the reconstruction: encode(decode(codes)) == codes (centroids encode to themselves or an equal-distance twin)
+    again = M.pq_encode(M.pq_decode(exact, cent.half()), cent, impl=L.IMPL_GRID)
+    assert torch.equal(M.pq_decode(again, cent.half()), M.pq_decode(exact, cent.half()))
+
+
 def test_attn_two_bit_config_fast_path(M, dtype, bs, nh, nh_k, nk, r):
     """M=32, d_m=4 ('2-bit', BASELINE config 5): the dedicated fast kernel (attn_fast_dm4.cu) against the oracle."""
     from million_b200 import _lib as L
