@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MILLION_ABI_VERSION 5
+#define MILLION_ABI_VERSION 6
 
 typedef void* million_stream_t; /* cudaStream_t */
 
@@ -210,11 +210,19 @@ typedef struct million_attn_params {
     const uint8_t* v_out_idx;
     const void* v_out_val;
     int64_t v_out_head_stride;
+
+    /* Split-KV across GPUs fused into this launch (MILLION_ATTN_FUSED_SPLITKV): instead of returning the rank's partial state,
+     * the last CTA of every (b, kv-head) group stores it straight into every peer's symmetric buffer over NVLink, the last
+     * group publishes this rank's sequence flag, waits for the flags of all ranks (bounded spin) and writes the merged
+     * result to `out`.  Same buffers and protocol as million_splitkv_push_merge (rows = bs * nh); `p2p_state` is the
+     * million_splitkv_state_bytes() block prepared once by million_splitkv_state_init. */
+    void* p2p_state;
 } million_attn_params;
 
 #define MILLION_MAX_OUTLIERS 8
 
 #define MILLION_ATTN_PARTIAL_ONLY 1
+#define MILLION_ATTN_FUSED_SPLITKV 2
 
 /* Codebook preparation for the FAST decode-attention kernel: both codebooks as fp16 pairs in the kernel's gather
  * order (d=128, M in {32, 64}, C=256 only: returns 0 bytes / MILLION_ERR_UNSUPPORTED otherwise).  One tiny launch; callers
@@ -239,6 +247,12 @@ int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, vo
  * this process (e.g. torch.distributed._symmetric_memory buffer_ptrs), each million_splitkv_symmetric_bytes() big and
  * zero-initialised once.  `state`: 16 bytes of zero-initialised device memory private to this rank. */
 int64_t million_splitkv_symmetric_bytes(int world, int64_t rows, int d);
+/* Protocol state of one rank: [calls completed u32 | ticket i32 | error i32 | pad | rank i32 | world i32 | rows i32 | pad | peer pointers x 8].
+ * million_splitkv_state_init zeroes it and records rank, world, rows (= bs * nh of the calls it will serve) and the peers'
+ * symmetric buffers (asynchronous on `stream`);
+ * million_splitkv_push_merge only needs its first 16 bytes. */
+int64_t million_splitkv_state_bytes(void);
+int million_splitkv_state_init(void* state, void* const* peer_bases_host, int rank, int world, int64_t rows, million_stream_t stream);
 int million_splitkv_push_merge(const float* local_partial, void* const* peer_bases_host, int rank, int world, int64_t rows, int d,
                                void* out, int io_dtype, void* state, million_stream_t stream);
 

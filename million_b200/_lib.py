@@ -14,7 +14,8 @@ MILLION_OK, MILLION_ERR_INVALID, MILLION_ERR_UNSUPPORTED, MILLION_ERR_CUDA = 0, 
 V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_FAST, IMPL_GRID = 0, 1, 2, 3
 ATTN_PARTIAL_ONLY = 1
-ABI_VERSION = 5
+ATTN_FUSED_SPLITKV = 2
+ABI_VERSION = 6
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
 
@@ -40,6 +41,7 @@ class AttnParams(ctypes.Structure):
         ("k_out", c_i32), ("v_out", c_i32),
         ("k_out_idx", c_vp), ("k_out_val", c_vp), ("k_out_head_stride", c_i64),
         ("v_out_idx", c_vp), ("v_out_val", c_vp), ("v_out_head_stride", c_i64),
+        ("p2p_state", c_vp),
     ]
 
 
@@ -69,6 +71,8 @@ SIGNATURES = {
     "million_pq_decode_attn": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),
     "million_lse_merge": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
     "million_splitkv_symmetric_bytes": (c_i64, [ctypes.c_int, c_i64, ctypes.c_int]),
+    "million_splitkv_state_bytes": (c_i64, []),
+    "million_splitkv_state_init": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, c_vp]),
     "million_splitkv_push_merge": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp]),
     "million_window_append": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, c_vp]),

@@ -16,7 +16,8 @@ struct AttnArgs {
     const void* k_res;
     const void* v_res;
     void* out;
-    float* partial_out;   // PARTIAL_ONLY target or nullptr
+    float* partial_out;   // PARTIAL_ONLY target or nullptr; with bit 0 set: the P2PState block of the fused split-KV exchange
+                          // (tagged pointer on purpose: one more kernel parameter measurably perturbs the main loop's allocation)
     int* counters;        // (bs*nh_k) arrival tickets, zero on entry and on exit
     float* parts;         // (bs*nh, n_parts, d+2) fp32: [o_unnormalised | m (log2 units) | l]
     int64_t k_head_stride, v_head_stride, v_ld;
@@ -73,6 +74,22 @@ constexpr int kMergeScratch = 3 * 2048 + 64;
 // floats per partial-state row [o (d) | m | l] in the kernels' workspace, padded to 16 bytes so that rows can be bulk-copied
 __host__ __device__ __forceinline__ constexpr int part_stride(int d) { return (d + 2 + 3) & ~3; }
 
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// device-memory block of the split-KV protocol (million_splitkv_state_init): read only on the merge path
+struct P2PState {
+    unsigned counter; int ticket; int err; int pad0;
+    int rank, world, rows, pad1;     // rows = bs * nh of the calls this block is used with
+    unsigned char* peer[8];
+};
+
 struct MergeArgs {
     int nh, nh_k, n_parts, d;
     const float* parts;
@@ -90,6 +107,18 @@ __device__ __forceinline__ void dbg_stamp_m(const MergeArgs& a, int slot) { dbg_
 template <typename T>
 __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, int n_parts, float* scr) {
     const int G = a.nh / a.nh_k;
+    const bool p2p = (reinterpret_cast<uintptr_t>(a.partial_out) & 1) != 0;
+    P2PState* const ps = reinterpret_cast<P2PState*>(reinterpret_cast<uintptr_t>(a.partial_out) & ~(uintptr_t)1);
+    unsigned p2p_seq = 0, p2p_par = 0;
+    int p2p_rank = 0, p2p_world = 0, p2p_rows = 0;
+    size_t p2p_slot = 0;
+    if (p2p) {
+        p2p_rows = ps->rows;
+        p2p_slot = (size_t)p2p_rows * (a.d + 2);   // the counter moves only after every group of this launch has pushed: all group-last CTAs read the same value
+        p2p_seq = *reinterpret_cast<volatile unsigned*>(&ps->counter) + 1;
+        p2p_par = p2p_seq & 1;
+        p2p_rank = ps->rank; p2p_world = ps->world;
+    }
     const int slots = a.n_parts;
     const int stride = part_stride(a.d);    // workspace rows
     const int ostride = a.d + 2;            // rows of partial_out (public layout)
@@ -204,7 +233,16 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
                 for (; i < n_parts; ++i) acc = fmaf(__ldcg(src + (int64_t)i * stride), w[i], acc);
             }
             const int h = h0 + g;
-            if (a.partial_out) {
+            if (p2p) {
+                // fused split-KV: this rank's state of row (b, h) goes straight into slot [parity][rank] of EVERY rank's receive
+                // buffer (NVLink stores, consecutive k = coalesced); layout of million_splitkv_push_merge
+                const size_t off = ((size_t)p2p_par * p2p_world + p2p_rank) * p2p_slot + (size_t)(b * a.nh + h) * ostride;
+                for (int r = 0; r < p2p_world; ++r) {
+                    float* dst = reinterpret_cast<float*>(ps->peer[r] + 1024) + off;
+                    dst[k] = acc;
+                    if (k == 0) { dst[a.d] = hd[2 * g] * kLn2; dst[a.d + 1] = hd[2 * g + 1]; }
+                }
+            } else if (a.partial_out) {
                 a.partial_out[(int64_t)(b * a.nh + h) * ostride + k] = acc;
                 if (k == 0) {
                     a.partial_out[(int64_t)(b * a.nh + h) * ostride + a.d] = hd[2 * g] * kLn2;   // natural-log units
@@ -216,6 +254,79 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
             }
         }
         __syncthreads();
+    }
+    if (!p2p) return;
+    // ---------------------------------------------------------------- fused split-KV: publish, wait for the peers, final merge
+    // Ordering as in splitkv_p2p.cu: this block's peer stores -> bar.sync -> acq_rel ticket at gpu scope -> (the last group's
+    // block) release stores of the flags at system scope -> the peers' acquire loads.
+    int* sflag = reinterpret_cast<int*>(scr);
+    if (threadIdx.x == 0) {
+        int t;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(&ps->ticket) : "memory");
+        const int last = (t == p2p_rows / G - 1);     // groups = rows / (nh / nh_k)
+        if (last) {
+            ps->ticket = 0;
+            *reinterpret_cast<volatile unsigned*>(&ps->counter) = p2p_seq;
+        }
+        *sflag = last;
+    }
+    __syncthreads();
+    if (!*sflag) return;
+    if ((int)threadIdx.x < p2p_world) {
+        st_release_sys(reinterpret_cast<unsigned*>(ps->peer[threadIdx.x] + 128 * p2p_rank), p2p_seq);   // every group of this rank has pushed
+        const unsigned* f = reinterpret_cast<const unsigned*>(ps->peer[p2p_rank] + 128 * threadIdx.x);
+        int spins = 0;
+        while ((int)(ld_acquire_sys(f) - p2p_seq) < 0) {      // bounded: a dead peer must not hang the GPU
+            __nanosleep(100);
+            if (++spins > (1 << 23)) { ps->err = 1; break; }
+        }
+    }
+    __syncthreads();
+    // final merge of rows x world parts by this one block, arranged so that every phase is ONE round of independent L2 loads:
+    // (1) all (m, l) pairs, (2) weights per row, (3) the outputs, 4 x world loads in flight per thread
+    const float* recv = reinterpret_cast<const float*>(ps->peer[p2p_rank] + 1024) + (size_t)p2p_par * p2p_world * p2p_slot;
+    const int W = p2p_world, os = a.d + 2;
+    float* sm_m = scr;                 // [rows][W]   (rows * W <= 2048 is checked on the host: rows <= 256)
+    float* sm_l = scr + 2048;          // [rows][W]
+    float* sm_w = scr + 4096;          // [rows][W] weights / den
+    for (int i = threadIdx.x; i < p2p_rows * W; i += blockDim.x) {
+        const int row = i / W, g = i - row * W;
+        const float* p = recv + (size_t)g * p2p_slot + (size_t)row * os;
+        sm_m[i] = __ldcg(p + a.d);
+        sm_l[i] = __ldcg(p + a.d + 1);
+    }
+    __syncthreads();
+    for (int row = threadIdx.x; row < p2p_rows; row += blockDim.x) {
+        float mstar = -INFINITY, den = 0.f;
+        for (int g = 0; g < W; ++g)
+            if (sm_l[row * W + g] > 0.f) mstar = fmaxf(mstar, sm_m[row * W + g]);
+        for (int g = 0; g < W; ++g) {
+            const float l = sm_l[row * W + g];
+            const float w = l > 0.f ? __expf(sm_m[row * W + g] - mstar) : 0.f;
+            sm_w[row * W + g] = w;
+            den += l * w;
+        }
+        const float inv = den > 0.f ? 1.f / den : 0.f;
+        for (int g = 0; g < W; ++g) sm_w[row * W + g] *= inv;
+    }
+    __syncthreads();
+    const int total = p2p_rows * a.d;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) {
+                const int row = i / a.d, k = i - row * a.d;
+                const float* p = recv + (size_t)row * os + k;
+                for (int g = 0; g < W; ++g) acc[u] = fmaf(__ldcg(p + (size_t)g * p2p_slot), sm_w[row * W + g], acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) reinterpret_cast<T*>(a.out)[i] = io<T>::from_f(acc[u]);
+        }
     }
 }
 

@@ -220,6 +220,10 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     MILLION_REQUIRE(p->nk >= 0 && p->r >= 0 && p->r <= p->res_len, "attn: bad nk/r (nk=%d r=%d res_len=%d)", p->nk, p->r, p->res_len);
     if (p->bs == 0) return MILLION_OK;
     const bool partial_only = (p->flags & MILLION_ATTN_PARTIAL_ONLY) != 0;
+    const bool fused_splitkv = (p->flags & MILLION_ATTN_FUSED_SPLITKV) != 0;
+    MILLION_REQUIRE(!(partial_only && fused_splitkv), "attn: PARTIAL_ONLY and FUSED_SPLITKV exclude each other");
+    if (fused_splitkv) MILLION_REQUIRE((int64_t)p->bs * p->nh <= 256, "attn: fused split-KV serves at most 256 (batch, head) rows");
+    if (fused_splitkv) MILLION_REQUIRE(p->p2p_state != nullptr && ((uintptr_t)p->p2p_state & 15) == 0, "attn: fused split-KV needs the (16-byte aligned) state block of million_splitkv_state_init");
     MILLION_REQUIRE(p->q && p->k_cent && p->v_cent && p->workspace, "attn: null pointer");
     MILLION_REQUIRE(partial_only ? (p->partial != nullptr) : (p->out != nullptr), "attn: missing output pointer");
     MILLION_REQUIRE(p->nk == 0 || (p->k_codes && p->v_codes), "attn: null code pointer");
@@ -254,6 +258,7 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     if (a.units_per_split < 4) a.units_per_split = 4;
     MILLION_REQUIRE(S + 1 <= 1024, "attn: at most 1023 splits");
     a.scale_log2 = kLog2e / sqrtf((float)p->d);
+    if (fused_splitkv) a.partial_out = reinterpret_cast<float*>(reinterpret_cast<uintptr_t>(p->p2p_state) | 1);   // tagged: see AttnArgs
     if (p->nk > 0 && p->k_out > 0 && p->k_out_idx && p->k_out_val) {
         MILLION_REQUIRE(p->k_out <= MILLION_MAX_OUTLIERS && p->d <= 256, "attn: k_out %d > %d or d > 256", p->k_out, MILLION_MAX_OUTLIERS);
         MILLION_REQUIRE(p->k_out_head_stride >= (int64_t)p->nk * p->k_out, "attn: k_out_head_stride too small");

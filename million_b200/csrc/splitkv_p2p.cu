@@ -11,7 +11,9 @@
 //   [1024, ...)      recv[parity 2][world][rows][d+2] fp32
 // Double buffering by sequence parity is enough: a rank can publish call n+1 only after it finished call n (stream order),
 // and a peer can start call n+2 only after it has seen everybody's call n+1.
-#include "common.cuh"
+#include <string.h>
+
+#include "attn_common.cuh"
 
 namespace million {
 
@@ -26,15 +28,6 @@ struct P2PArgs {
     int64_t rows;
     int rank, world, d;
 };
-
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 template <typename T>
 __global__ void __launch_bounds__(128) splitkv_push_merge_kernel(const P2PArgs a) {
@@ -124,6 +117,21 @@ extern "C" {
 
 int64_t million_splitkv_symmetric_bytes(int world, int64_t rows, int d) {
     return 1024 + (int64_t)2 * world * rows * (d + 2) * 4;
+}
+
+int64_t million_splitkv_state_bytes(void) { return (int64_t)sizeof(P2PState); }
+
+int million_splitkv_state_init(void* state, void* const* peer_bases_host, int rank, int world, int64_t rows, million_stream_t stream) {
+    MILLION_REQUIRE(state && peer_bases_host, "splitkv_state_init: null pointer");
+    MILLION_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "splitkv_state_init: world must be 1..8");
+    P2PState h;
+    memset(&h, 0, sizeof h);
+    MILLION_REQUIRE(rows > 0 && rows < (1ll << 31), "splitkv_state_init: bad rows");
+    h.rank = rank; h.world = world; h.rows = (int)rows;
+    for (int g = 0; g < world; ++g) h.peer[g] = (unsigned char*)peer_bases_host[g];
+    // pageable source: the copy is staged by the runtime before the call returns, so the stack object may go away
+    MILLION_CUDA_OK(cudaMemcpyAsync(state, &h, sizeof h, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return MILLION_OK;
 }
 
 /* state: device memory of 16 bytes, zero-initialised by the caller once: [counter u32 | ticket i32 | err i32 | pad] */

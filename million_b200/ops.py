@@ -263,13 +263,14 @@ def prepare_codebooks(k_cent, v_cent):
 
 def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=None, v_layout=L.V_ROWMAJOR,
                    v_page_ids=None, page_size=0, out=None, partial=None, n_splits=0, impl=L.IMPL_AUTO, workspace=None,
-                   prepared=None, k_outliers=None, v_outliers=None):
+                   prepared=None, k_outliers=None, v_outliers=None, p2p=None):
     """One decode-attention call (include/million_b200.h: million_pq_decode_attn).
 
     q (bs, nh, 1, d) | (bs, nh, d); k_codes (bs, nh_k, >=nk, M) uint8 (head stride taken from the tensor);
     v_codes: rowmajor (bs, nh_k, >=nk, M) | transposed (bs, nh_k, M, >=nk) | paged pool (pages, M, page_size);
     k_res/v_res (bs, nh_k, Lt, d).  Returns (bs, nh, 1, d) in q's dtype, or fills `partial` (bs, nh, d+2) fp32.
     k_outliers / v_outliers: optional (idx, val) side stores (bs, nh_k, >=nk, k_out) uint8 / q's dtype (extension).
+    p2p = state tensor prepared by splitkv_state(): split-KV across GPUs fused into this launch (sharding.SplitKVPeerGroup).
     """
     _need_cuda(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res)
     bs, nh = q.shape[0], q.shape[1]
@@ -283,6 +284,10 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
     p = L.AttnParams()
     p.struct_size = ctypes.sizeof(L.AttnParams)
     p.io_dtype, p.impl, p.flags = _dt(q), impl, (L.ATTN_PARTIAL_ONLY if partial is not None else 0)
+    if p2p is not None:
+        assert partial is None
+        p.flags |= L.ATTN_FUSED_SPLITKV
+        p.p2p_state = p2p.data_ptr()
     p.bs, p.nh, p.nh_k, p.d, p.M, p.C, p.nk, p.r = bs, nh, nh_k, d, M, C, nk, r
     p.q = q.data_ptr()
     if nk:
@@ -346,6 +351,17 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
         ret = out
     L.check(L.lib().million_pq_decode_attn(ctypes.byref(p), _stream(q)))
     return ret
+
+
+def splitkv_state(peer_ptrs, rank, rows, device):
+    """Protocol state block of one rank for million_splitkv_push_merge / the fused split-KV attention (zeroed; rank, world, rows = bs * nh
+    and the peers' symmetric-buffer pointers recorded)."""
+    world = len(peer_ptrs)
+    state = torch.zeros(L.lib().million_splitkv_state_bytes(), dtype=torch.uint8, device=device)
+    arr = (ctypes.c_void_p * world)(*peer_ptrs)
+    L.check(L.lib().million_splitkv_state_init(_ptr(state), ctypes.cast(arr, ctypes.c_void_p), rank, world, rows, _stream(state)))
+    torch.cuda.current_stream(state.device).synchronize()
+    return state
 
 
 def lse_merge(parts, d, out_dtype):

@@ -79,7 +79,8 @@ class SplitKVPeerGroup:
         self.handle = symm.rendezvous(self.buf, self.group)
         ptrs = list(self.handle.buffer_ptrs)
         self._peer_array = (ctypes.c_void_p * self.world)(*ptrs)
-        self.state = torch.zeros(4, dtype=torch.int32, device=self.buf.device)
+        from . import ops
+        self.state = ops.splitkv_state(ptrs, self.rank, rows, self.buf.device)
         self.partial = torch.empty(rows, d + 2, dtype=torch.float32, device=self.buf.device)
         torch.cuda.synchronize()
         dist.barrier(self.group)
@@ -97,12 +98,18 @@ class SplitKVPeerGroup:
                                                    ctypes.c_void_p(self.state.data_ptr()), st))
         return out
 
-    def decode_attn(self, q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, out=None, **attn_kw):
+    def decode_attn(self, q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, out=None, fused=False, **attn_kw):
+        """fused=True: ONE launch per layer — the attention kernel's own merge epilogue pushes this rank's state to the peers,
+        waits for theirs and writes the merged result (MILLION_ATTN_FUSED_SPLITKV); otherwise attention + million_splitkv_push_merge."""
         from . import ops
         bs, nh, d = q.shape[0], q.shape[1], q.shape[-1]
+        if fused:
+            assert bs * nh == self.rows
+            return ops.pq_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, out=out,
+                                      p2p=self.state, **attn_kw)
         ops.pq_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, partial=self.partial, **attn_kw)
         o = self.merge(None if out is None else out.view(bs * nh, d))
         return o.view(bs, nh, 1, d)
 
     def timed_out(self):
-        return bool(self.state[2].item())
+        return bool(self.state.view(torch.int32)[2].item())

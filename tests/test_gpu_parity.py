@@ -292,6 +292,28 @@ def test_partial_and_lse_merge_equals_single_call(M):
     np.testing.assert_allclose(merged.float().cpu().numpy(), full.float().cpu().numpy(), atol=1e-3, rtol=5e-3)
 
 
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("bs,nh,nh_k,nk", [(1, 8, 2, 3000), (2, 4, 4, 700), (8, 8, 2, 4100)])
+def test_fused_splitkv_world1_equals_plain_call(M, impl, bs, nh, nh_k, nk):
+    """MILLION_ATTN_FUSED_SPLITKV with a world of one rank (the protocol degenerates to push-to-self, flag, merge of one part): same
+    result as the plain call, on consecutive launches (sequence parity flips), no timeout.  The multi-rank run is
+    tools/splitkv_nccl.py --p2p --fused."""
+    import ctypes
+    from million_b200 import _lib as L
+    inp = O.make_inputs(bs=bs, nh=nh, nh_k=nh_k, nk=nk, seed=5)
+    t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    rows, d = bs * nh, 128
+    buf = torch.zeros(L.lib().million_splitkv_symmetric_bytes(1, rows, d), dtype=torch.uint8, device="cuda")
+    state = M.splitkv_state([buf.data_ptr()], 0, rows, buf.device)
+    for r in (128, 17, 1):
+        plain = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl)
+        fused = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl,
+                                 p2p=state)
+        np.testing.assert_allclose(fused.float().cpu().numpy(), plain.float().cpu().numpy(), atol=2e-3, rtol=1e-2)
+    st = state.view(torch.int32).cpu().numpy()
+    assert st[0] == 3 and st[1] == 0 and st[2] == 0          # three completed calls, ticket back to zero, no timeout
+
+
 def test_full_size_llama31_8b_32k_properties(M):
     """BASELINE config 2 at full size (bs 1, 32q/8kv heads, 32K ctx): checked against a torch fp32 restatement on the
     GPU (de-quantise + softmax), and the size-independent property 'all value codes equal -> output is that centroid
@@ -317,8 +339,6 @@ def test_full_size_llama31_8b_32k_properties(M):
     torch.testing.assert_close(out2.float(), want, atol=ATOL, rtol=RTOL)
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("bs,nh,nh_k,nk,r", [(1, 32, 8, 5000, 128), (2, 8, 8, 777, 17), (1, 16, 8, 64, 1), (1, 32, 4, 2100, 40), (2, 4, 4, 0, 9)])
 def test_full_size_encode_grid_equals_exact_encoder(M):
     """BASELINE config 2/3 prefill shape (8 kv-heads x 32768 tokens, M=64): the candidate-grid encoder, the tensor-core encoder and
     the exact CUDA-core encoder must agree on every one of the 16.8 M codes (the oracle is too slow at this size: the exact
@@ -336,6 +356,8 @@ def test_full_size_encode_grid_equals_exact_encoder(M):
     assert torch.equal(M.pq_decode(again, cent.half()), M.pq_decode(exact, cent.half()))
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bs,nh,nh_k,nk,r", [(1, 32, 8, 5000, 128), (2, 8, 8, 777, 17), (1, 16, 8, 64, 1), (1, 32, 4, 2100, 40), (2, 4, 4, 0, 9)])
 def test_attn_two_bit_config_fast_path(M, dtype, bs, nh, nh_k, nk, r):
     """M=32, d_m=4 ('2-bit', BASELINE config 5): the dedicated fast kernel (attn_fast_dm4.cu) against the oracle."""
     from million_b200 import _lib as L

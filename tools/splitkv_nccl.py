@@ -7,7 +7,7 @@ import torch, torch.distributed as dist
 from million_b200 import ops, sharding
 
 ap = argparse.ArgumentParser(); ap.add_argument("--ctx", type=int, default=131072); ap.add_argument("--layers", type=int, default=32)
-ap.add_argument("--steps", type=int, default=20); ap.add_argument("--graph", action="store_true"); ap.add_argument("--p2p", action="store_true"); a = ap.parse_args()
+ap.add_argument("--steps", type=int, default=20); ap.add_argument("--graph", action="store_true"); ap.add_argument("--p2p", action="store_true"); ap.add_argument("--fused", action="store_true", help="with --p2p: exchange inside the attention kernel (one launch per layer)"); a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1: dist.init_process_group("nccl", device_id=dev)
@@ -25,7 +25,7 @@ r_local = r if rank == world - 1 else 0
 full = ops.pq_decode_attn(q, kc, vc, kcent, vcent, kres, vres, r)
 peer = sharding.SplitKVPeerGroup(NH, D, torch.float16) if (a.p2p and world > 1) else None
 if peer is not None:
-    out = peer.decode_attn(q, kcl, vcl, kcent, vcent, kres, vres, r_local).clone()
+    out = peer.decode_attn(q, kcl, vcl, kcent, vcent, kres, vres, r_local, fused=a.fused).clone()
 elif world > 1:
     out = sharding.splitkv_decode_attn(q, kcl, vcl, kcent, vcent, kres, vres, r_local)
 else:
@@ -37,7 +37,7 @@ outbuf = torch.empty(1, NH, 1, D, dtype=torch.float16, device=dev)
 def step():
     for i in range(a.layers):
         k_, v_ = layers[i % len(layers)]
-        if peer is not None: peer.decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, out=outbuf)
+        if peer is not None: peer.decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, out=outbuf, fused=a.fused)
         elif world > 1: sharding.splitkv_decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local)
         else: ops.pq_decode_attn(q, k_, v_, kcent, vcent, kres, vres, r)
 for _ in range(3): step()
@@ -80,6 +80,6 @@ if peer is not None:
     if rank == 0: print(f"  exchange+merge kernel alone: {tm.item():.1f} us per call (eager launches); local partial attention alone: {ta.item():.1f} us per layer")
 if rank == 0:
     ms = t.item(); alg = 2 * NHK * nk * M + 2 * NHK * r * D * 2
-    print(f"split-KV world={world} ctx={a.ctx} graph={a.graph} p2p={a.p2p} timed_out={peer.timed_out() if peer is not None else None}: max|merged - single| = {err:.2e}; {ms:.3f} ms per {a.layers}-layer token -> {1e3/ms:.1f} tok/s; "
+    print(f"split-KV world={world} ctx={a.ctx} graph={a.graph} p2p={a.p2p} fused={a.fused} timed_out={peer.timed_out() if peer is not None else None}: max|merged - single| = {err:.2e}; {ms:.3f} ms per {a.layers}-layer token -> {1e3/ms:.1f} tok/s; "
           f"{alg * a.layers / (ms * 1e-3) / 1e9:.0f} GB/s aggregate algorithmic")
 if world > 1: dist.destroy_process_group()
