@@ -191,17 +191,22 @@ __global__ void __launch_bounds__(kGridThreads, 1) encode_grid_kernel(const T* _
     // each thread walks its vectors with the NEXT one's 4 input elements already in flight (the loads are 256-byte strided across
     // the warp: their L2 latency would otherwise sit in front of every lookup chain)
     using Raw = typename std::conditional<sizeof(T) == 2, uint2, float4>::type;
-    auto row = [&](long long v) {
-        const int head = (int)(v / n_tokens), t = (int)(v - (long long)head * n_tokens);
-        return reinterpret_cast<const Raw*>(x + head * x_head_stride + (int64_t)t * d + 4 * grp);
+    // (head, token) of a vector index advance incrementally: a 64-bit division per vector was a third of the loop's instructions
+    auto row = [&](int head, int t) { return reinterpret_cast<const Raw*>(x + head * x_head_stride + (int64_t)t * d + 4 * grp); };
+    auto advance = [&](int& head, int& t) {
+        t += kGridThreads;
+        if (t >= n_tokens) { const int q = t / n_tokens; head += q; t -= q * n_tokens; }     // 32-bit, and only when a head boundary is crossed
     };
     long long v = v0 + tid;
+    int head = (int)(v / n_tokens), t = (int)(v - (long long)head * n_tokens);
     Raw raw = {};
-    if (v < v1) raw = *row(v);
+    if (v < v1) raw = *row(head, t);
     while (v < v1) {
         const long long vn = v + kGridThreads;
+        int hn = head, tn = t;
+        advance(hn, tn);
         Raw nxt = {};
-        if (vn < v1) nxt = *row(vn);
+        if (vn < v1) nxt = *row(hn, tn);
         float p[4];
         if constexpr (sizeof(T) == 2) {
             const float2 a = io<T>::to_f2(raw.x), b = io<T>::to_f2(raw.y);
@@ -209,12 +214,11 @@ __global__ void __launch_bounds__(kGridThreads, 1) encode_grid_kernel(const T* _
         } else {
             p[0] = raw.x; p[1] = raw.y; p[2] = raw.z; p[3] = raw.w;
         }
-        const int head = (int)(v / n_tokens), t = (int)(v - (long long)head * n_tokens);
         const int c0 = grid_code(p[0], p[1], hdr, tab, cs, C);
         const int c1 = grid_code(p[2], p[3], hdr + 8, tab + kGridCells, cs + 256, C);
         dst.put2(head, t, 2 * grp, c0, c1);
         raw = nxt;
-        v = vn;
+        v = vn; head = hn; t = tn;
     }
 }
 
