@@ -21,10 +21,6 @@
 
 namespace million {
 
-#ifndef MILLION_QK_PARTS
-#define MILLION_QK_PARTS 1
-#endif
-constexpr int kQkParts = MILLION_QK_PARTS;   // 1 = the 64 QK gathers of a tile fully unrolled
 
 // ------------------------------------------------------------------------------------------------
 // Codebook preparation (once per codebook): fp16 tables in the column order the kernel gathers with.
@@ -298,29 +294,13 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                     }
                 }
             };
-            if constexpr (kQkParts == 1) {
+            {
                 uint32_t words[16];
 #pragma unroll
                 for (int w = 0; w < 16; ++w) words[w] = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));   // word (w + rot) % 16 of my row
                 if (!(a.dbg_mode & 1))
 #pragma unroll
                     for (int w = 0; w < 16; ++w) qk_gathers(words[w], koff[w]);
-            } else {
-                // rolled in kQkParts passes (smaller loop body; the per-word constants are recomputed)
-                constexpr int kPer = 16 / kQkParts;
-#pragma unroll 1
-                for (int part = 0; part < kQkParts; ++part) {
-                    uint32_t words[kPer], kf[kPer];
-#pragma unroll
-                    for (int i = 0; i < kPer; ++i) {
-                        const uint32_t Wl = (uint32_t)(part * kPer + i + rot) & 15u;
-                        words[i] = lds32(ksp, lane * kRowBytes + (Wl << 2));
-                        kf[i] = G == 4 ? (Wl * 0x0808u + 0x8000u) : (Wl * 0x0404u + 0x4000u);
-                    }
-                    if (!(a.dbg_mode & 1))
-#pragma unroll
-                        for (int i = 0; i < kPer; ++i) qk_gathers(words[i], kf[i]);
-                }
             }
             if constexpr (OUT) {
 #pragma unroll

@@ -77,3 +77,26 @@ def test_page_manager_allocation_order_growth_and_limits():
     capped.allocate_pages(3)
     with pytest.raises(RuntimeError):
         capped.allocate_page()
+
+
+def test_page_manager_bulk_allocation_matches_sequential():
+    """allocate_pages(n) must hand out exactly what n allocate_page() calls would (lowest id first, reuse counted, pool grown),
+    dynamic_paged_pq_utils.py:65-135; PageManager is plain host logic and runs on a CPU pool."""
+    from million_b200.paged_pq_utils import PageManager
+    a = PageManager(64, initial_pages=8, M=4, device='cpu')
+    b = PageManager(64, initial_pages=8, M=4, device='cpu')
+    got = a.allocate_pages(5) + a.allocate_pages(9)            # the second call has to grow the pool
+    want = [b.allocate_page() for _ in range(14)]
+    assert got == want == list(range(14))
+    for pm in (a, b):
+        pm.free_page(3); pm.free_page(11); pm.free_page(0)
+    assert a.allocate_pages(4) == [b.allocate_page() for _ in range(4)] == [0, 3, 11, 14]
+    sa, sb = a.get_stats(), b.get_stats()
+    for k in ('allocated_pages', 'page_reuse_count', 'total_allocations'):      # pool growth differs by design (bulk grows by exactly what it needs)
+        assert sa[k] == sb[k], k
+    assert a.allocated_pages[3]['allocation_count'] == 1 and sa['page_reuse_count'] == 3
+    assert a.allocate_pages(0) == []
+    capped = PageManager(64, initial_pages=4, max_pages=6, M=4, device='cpu')
+    capped.allocate_pages(6)
+    with pytest.raises(RuntimeError):
+        capped.allocate_pages(1)
