@@ -243,21 +243,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 const bool ok = tile < n_tiles && tok < t1;
                 const int64_t rec = hb * a.ko_head_stride + (int64_t)(ok ? tok : t0) * a.k_out;
                 const unsigned short* vals = reinterpret_cast<const unsigned short*>(a.ko_val) + rec;
-                if (a.k_out == 2) {
-                    ko_dims = __ldg(reinterpret_cast<const unsigned short*>(a.ko_idx + rec));
-                    ko_v01 = __ldg(reinterpret_cast<const uint32_t*>(vals));
-                } else if (a.k_out == 4) {
-                    ko_dims = __ldg(reinterpret_cast<const uint32_t*>(a.ko_idx + rec));
-                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(vals));
-                    ko_v01 = v.x; ko_v23 = v.y;
-                } else if (a.k_out == 1) {
-                    ko_dims = __ldg(a.ko_idx + rec);
-                    ko_v01 = __ldg(vals);
-                } else {
-                    ko_dims = (uint32_t)__ldg(a.ko_idx + rec) | ((uint32_t)__ldg(a.ko_idx + rec + 1) << 8) | ((uint32_t)__ldg(a.ko_idx + rec + 2) << 16);
-                    ko_v01 = (uint32_t)__ldg(vals) | ((uint32_t)__ldg(vals + 1) << 16);
-                    ko_v23 = __ldg(vals + 2);
-                }
+                ko_load(a.ko_idx + rec, vals, a.k_out, ko_dims, ko_v01, ko_v23);
             }
         };
         ko_fetch(warp);
