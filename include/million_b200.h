@@ -215,7 +215,8 @@ typedef struct million_attn_params {
      * the last CTA of every (b, kv-head) group stores it straight into every peer's symmetric buffer over NVLink, the last
      * group publishes this rank's sequence flag, waits for the flags of all ranks (bounded spin) and writes the merged
      * result to `out`.  Same buffers and protocol as million_splitkv_push_merge (rows = bs * nh); `p2p_state` is the
-     * million_splitkv_state_bytes() block prepared once by million_splitkv_state_init. */
+     * million_splitkv_state_bytes() block prepared once by million_splitkv_state_init.  EXPERIMENTAL: compiled only with
+     * -DMILLION_FUSED_SPLITKV (slower than the separate exchange launch so far); other builds return MILLION_ERR_UNSUPPORTED. */
     void* p2p_state;
 } million_attn_params;
 

@@ -18,7 +18,7 @@ STAMP = os.path.join(HERE, ".build_stamp")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("MILLION_NVCC_EXTRA", "").split()      # e.g. MILLION_NVCC_EXTRA=-DMILLION_FUSED_SPLITKV (experimental option)
 
 
 def sources():

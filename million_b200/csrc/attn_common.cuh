@@ -107,7 +107,14 @@ __device__ __forceinline__ void dbg_stamp_m(const MergeArgs& a, int slot) { dbg_
 template <typename T>
 __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, int n_parts, float* scr) {
     const int G = a.nh / a.nh_k;
+    // Compiled in only with -DMILLION_FUSED_SPLITKV: the mere presence of this path in the (out-of-line) merge function changes the
+    // register allocation of the attention kernels that call it and costs 2.5 % per launch at batch 8 (107.4 vs 104.8 us, A/B on
+    // one box), while the fused exchange itself is slower than the separate exchange launch.
+#ifdef MILLION_FUSED_SPLITKV
     const bool p2p = (reinterpret_cast<uintptr_t>(a.partial_out) & 1) != 0;
+#else
+    const bool p2p = false;
+#endif
     P2PState* const ps = reinterpret_cast<P2PState*>(reinterpret_cast<uintptr_t>(a.partial_out) & ~(uintptr_t)1);
     unsigned p2p_seq = 0, p2p_par = 0;
     int p2p_rank = 0, p2p_world = 0, p2p_rows = 0;

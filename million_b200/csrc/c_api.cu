@@ -222,6 +222,9 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     const bool partial_only = (p->flags & MILLION_ATTN_PARTIAL_ONLY) != 0;
     const bool fused_splitkv = (p->flags & MILLION_ATTN_FUSED_SPLITKV) != 0;
     MILLION_REQUIRE(!(partial_only && fused_splitkv), "attn: PARTIAL_ONLY and FUSED_SPLITKV exclude each other");
+#ifndef MILLION_FUSED_SPLITKV
+    if (fused_splitkv) MILLION_UNSUPPORTED("attn: this build has no fused split-KV exchange (experimental: rebuild with -DMILLION_FUSED_SPLITKV); use MILLION_ATTN_PARTIAL_ONLY + million_splitkv_push_merge");
+#endif
     if (fused_splitkv) MILLION_REQUIRE((int64_t)p->bs * p->nh <= 256, "attn: fused split-KV serves at most 256 (batch, head) rows");
     if (fused_splitkv) MILLION_REQUIRE(p->p2p_state != nullptr && ((uintptr_t)p->p2p_state & 15) == 0, "attn: fused split-KV needs the (16-byte aligned) state block of million_splitkv_state_init");
     MILLION_REQUIRE(p->q && p->k_cent && p->v_cent && p->workspace, "attn: null pointer");

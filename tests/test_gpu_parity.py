@@ -307,8 +307,13 @@ def test_fused_splitkv_world1_equals_plain_call(M, impl, bs, nh, nh_k, nk):
     state = M.splitkv_state([buf.data_ptr()], 0, rows, buf.device)
     for r in (128, 17, 1):
         plain = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl)
-        fused = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl,
-                                 p2p=state)
+        try:
+            fused = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl,
+                                     p2p=state)
+        except L.MillionError as e:
+            if e.status == L.MILLION_ERR_UNSUPPORTED:
+                pytest.skip("library built without -DMILLION_FUSED_SPLITKV (the default: the option is experimental)")
+            raise
         np.testing.assert_allclose(fused.float().cpu().numpy(), plain.float().cpu().numpy(), atol=2e-3, rtol=1e-2)
     st = state.view(torch.int32).cpu().numpy()
     assert st[0] == 3 and st[1] == 0 and st[2] == 0          # three completed calls, ticket back to zero, no timeout
