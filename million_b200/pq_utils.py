@@ -274,6 +274,10 @@ class DynamicPQCache(metaclass=Singleton):
             self.value_cent = value_cent.contiguous()
         self._key_cent_f32 = self.key_cent.to(device=self.device, dtype=torch.float32).contiguous()
         self._value_cent_f32 = self.value_cent.to(device=self.device, dtype=torch.float32).contiguous()
+        # encoder tables are built here, on the caller's stream, not lazily inside the first flush (which may run on the side
+        # stream): every later use is ordered after this point
+        for c in {id(self._key_cent_f32): self._key_cent_f32, id(self._value_cent_f32): self._value_cent_f32}.values():
+            ops.prepare_encoder_grid(c)
 
     def _attn_cents(self, dtype):
         """Centroids in the query dtype for the attention kernel (main_pq.py:258-260 casts them to the model dtype)."""
