@@ -256,3 +256,24 @@ def test_paged_cache_with_outliers(M):
                                                 kout=(ki.cpu().numpy(), f(kv)), vout=vout)
                 np.testing.assert_allclose(f(out), ref, atol=ATOL, rtol=RTOL)
     Singleton.clear_instance()
+
+
+@pytest.mark.parametrize("name,k_out,Mm", [("m64k2", 2, 64), ("m32k1", 1, 32), ("m64k4", 4, 64)])
+def test_committed_outlier_vectors(M, name, k_out, Mm):
+    """the CUDA path against tests/golden/outlier_golden.npz: records and codes bit-exact, attention within the north-star tolerance
+    (generic kernel: K and V records; fast kernel: K records only)"""
+    import os
+    from million_b200 import _lib as L
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "outlier_golden.npz"))
+    X, C = torch.from_numpy(g[f"{name}_X"]).cuda(), torch.from_numpy(g[f"{name}_C"]).cuda()
+    codes, idx, val = M.pq_encode_outliers(X, C, k_out)
+    assert np.array_equal(codes.cpu().numpy(), g[f"{name}_codes"]) and np.array_equal(idx.cpu().numpy(), g[f"{name}_idx"])
+    assert np.array_equal(val.cpu().numpy(), g[f"{name}_val"])
+    dv = lambda k: torch.from_numpy(g[f"{name}_{k}"]).cuda()
+    out = M.pq_decode_attn(dv("q"), codes, dv("vcodes"), C.half(), C.half(), dv("kres"), dv("vres"), 9, impl=L.IMPL_GENERIC,
+                           k_outliers=(idx, val), v_outliers=(dv("vidx"), dv("vval")))
+    np.testing.assert_allclose(out.float().cpu().numpy(), g[f"{name}_attn"], atol=ATOL, rtol=RTOL)
+    ref_k = O.pq_decode_attn_outliers(g[f"{name}_q"], g[f"{name}_codes"], g[f"{name}_vcodes"], g[f"{name}_C"], g[f"{name}_C"],
+                                      g[f"{name}_kres"], g[f"{name}_vres"], 9, kout=(g[f"{name}_idx"], g[f"{name}_val"]))
+    fast = M.pq_decode_attn(dv("q"), codes, dv("vcodes"), C.half(), C.half(), dv("kres"), dv("vres"), 9, impl=L.IMPL_FAST, k_outliers=(idx, val))
+    np.testing.assert_allclose(fast.float().cpu().numpy(), ref_k, atol=ATOL, rtol=RTOL)

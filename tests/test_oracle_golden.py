@@ -1,5 +1,7 @@
 """CPU: pin the oracle (oracle/pq_oracle.py) against fixtures produced by the reference's own code
 (tests/golden/make_golden.py -> reference_golden.npz)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -157,3 +159,16 @@ def test_outlier_oracle_attention_reduces_to_plain():
     b = O.pq_decode_attn_outliers(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], 9,
                                   kout=(zi, zv), vout=(zi, zv))
     np.testing.assert_allclose(a, b, atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name,k_out", [("m64k2", 2), ("m32k1", 1), ("m64k4", 4)])
+def test_outlier_oracle_reproduces_committed_vectors(name, k_out):
+    """tests/golden/outlier_golden.npz (made by tests/golden/make_outlier_golden.py from this oracle): the definition must not drift."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "outlier_golden.npz"))
+    codes, idx, val = O.pq_encode_outliers(g[f"{name}_X"], g[f"{name}_C"], k_out)
+    assert np.array_equal(codes, g[f"{name}_codes"]) and np.array_equal(idx, g[f"{name}_idx"]) and np.array_equal(val, g[f"{name}_val"])
+    assert idx[0, 0, 0].tolist() == list(range(k_out)) and idx[0, 0, 1].tolist() == list(range(k_out))      # all-equal rows: lowest dims
+    assert np.array_equal(O.pq_decode_outliers(codes, g[f"{name}_C"], idx, val), g[f"{name}_recon"])
+    attn = O.pq_decode_attn_outliers(g[f"{name}_q"], codes, g[f"{name}_vcodes"], g[f"{name}_C"], g[f"{name}_C"], g[f"{name}_kres"],
+                                     g[f"{name}_vres"], 9, kout=(idx, val), vout=(g[f"{name}_vidx"], g[f"{name}_vval"]))
+    np.testing.assert_allclose(attn, g[f"{name}_attn"], atol=1e-6, rtol=1e-6)
