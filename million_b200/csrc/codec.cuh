@@ -14,9 +14,10 @@ struct CodeDst {
 
     __device__ __forceinline__ int64_t offset(int head, int t, int m) const {
         if (page_ids) {
-            const int64_t tt = t0 + t;
-            const int64_t page = page_ids[head * page_ids_head_stride + tt / page_size];
-            return (page * M + m) * page_size + tt % page_size;
+            // token indices fit 32 bits (nk is an int32 in the attention call): 32-bit division instead of two 64-bit ones
+            const uint32_t tt = (uint32_t)(t0 + t), chunk = tt / (uint32_t)page_size, in_page = tt - chunk * (uint32_t)page_size;
+            const int64_t page = page_ids[head * page_ids_head_stride + chunk];
+            return (page * M + m) * page_size + in_page;
         }
         return head * head_stride + (t0 + t) * token_stride + m * m_stride;
     }
