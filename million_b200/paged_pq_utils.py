@@ -35,7 +35,7 @@ class PageManager:
         self.current_active_pages = min(initial_pages, self.preallocated_size)
         self.page_pool = torch.zeros((self.preallocated_size, M, page_size), dtype=torch.uint8, device=self.device)
         self._free = list(range(self.current_active_pages - 1, -1, -1))   # stack, lowest id on top
-        self.allocated_pages: Dict[int, Dict] = {}
+        self._allocated: Set[int] = set()         # allocated page ids; `allocated_pages` is the reference's dict view of it
         self.total_expansions = 0
         self.page_reuse_count = 0
         self.total_allocations = 0
@@ -44,6 +44,12 @@ class PageManager:
     @property
     def free_pages(self) -> Set[int]:
         return set(self._free)
+
+    @property
+    def allocated_pages(self) -> Dict[int, Dict]:
+        """The reference's bookkeeping dict (dynamic_paged_pq_utils.py:52-63), built on demand: a page that is allocated was
+        allocated exactly once since it was last freed."""
+        return {pid: {'allocation_count': 1} for pid in self._allocated}
 
     def _expand_page_pool(self, additional_pages: int = None, force_expansion: bool = False):
         if additional_pages is None:
@@ -76,7 +82,7 @@ class PageManager:
         if pid in self._ever_used:
             self.page_reuse_count += 1
         self._ever_used.add(pid)
-        self.allocated_pages[pid] = {'allocation_count': self.allocated_pages.get(pid, {}).get('allocation_count', 0) + 1}
+        self._allocated.add(pid)
         self.total_allocations += 1
         return pid
 
@@ -97,16 +103,15 @@ class PageManager:
         del self._free[-n:]
         self.page_reuse_count += len(self._ever_used.intersection(ids))
         self._ever_used.update(ids)
-        ap = self.allocated_pages
-        ap.update((pid, {'allocation_count': ap[pid]['allocation_count'] + 1 if pid in ap else 1}) for pid in ids)
+        self._allocated.update(ids)
         self.total_allocations += n
         return ids
 
     def free_page(self, page_id: int):
-        if page_id not in self.allocated_pages:
+        if page_id not in self._allocated:
             logger.warning(f"Attempting to free unallocated page {page_id}")
             return
-        del self.allocated_pages[page_id]
+        self._allocated.discard(page_id)
         self._free.append(page_id)
         self._free.sort(reverse=True)
 
@@ -116,7 +121,7 @@ class PageManager:
     def get_page(self, page_id: int) -> torch.Tensor:
         if not self._is_valid_page_id(page_id):
             raise ValueError(f"Invalid page_id {page_id}: must be within [0, {self.current_active_pages})")
-        if page_id not in self.allocated_pages:
+        if page_id not in self._allocated:
             raise ValueError(f"Page {page_id} is not allocated")
         return self.page_pool[page_id]
 
@@ -126,8 +131,8 @@ class PageManager:
         return {
             'initial_pages': self.initial_pages, 'current_active_pages': self.current_active_pages,
             'preallocated_size': self.preallocated_size, 'max_pages': self.max_pages,
-            'allocated_pages': len(self.allocated_pages), 'free_pages': len(self._free),
-            'utilization': len(self.allocated_pages) / self.current_active_pages if self.current_active_pages else 0,
+            'allocated_pages': len(self._allocated), 'free_pages': len(self._free),
+            'utilization': len(self._allocated) / self.current_active_pages if self.current_active_pages else 0,
             'memory_usage_mb': self.page_pool.numel() / (1024 * 1024),
             'page_reuse_count': self.page_reuse_count, 'total_allocations': self.total_allocations,
             'total_expansions': self.total_expansions,
@@ -392,12 +397,12 @@ class PagedPQCache(DynamicPQCache):
 
     # ---- stats API (paged_pq_utils.py:898-1078)
     def get_cache_stats(self) -> Dict:
-        pages = sum(len(pm.allocated_pages) for pm in self.page_managers)
+        pages = sum(len(pm._allocated) for pm in self.page_managers)
         return {
             'layer_num': self.layer_num, 'page_size': self.page_size, 'extended_residual_size': self.extended_residual_size,
             'seen_tokens': list(self.seen_tokens), 'residualed_tokens': list(self.residualed_tokens),
             'quantized_tokens': [s.len for s in self._k], 'total_pages_allocated': pages,
-            'pages_per_layer': [len(pm.allocated_pages) for pm in self.page_managers],
+            'pages_per_layer': [len(pm._allocated) for pm in self.page_managers],
             'pq_cache_bytes': self.pq_cache_size, 'residual_cache_bytes': self.residual_cache_size,
         }
 
