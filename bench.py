@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""bench.py — PQ decode-attention throughput on Llama-3.1-8B shapes (BASELINE.json configs[1]).
+"""bench.py — PQ decode-attention throughput on Llama-3.1-8B shapes (BASELINE.json configs[1]) plus, in `extra`, the other
+north_star configurations (128K split-KV, Llama-2-7B KV-head sharding with the outlier store, paged prefill + async flush,
+PQ encode, the reference's own CUDA kernel recompiled for sm_100a).
 
 A "step" = one decoded token: the PQ decode-attention hot path run for all 32 layers over a batch of sequences whose
 32K-token KV caches are resident as PQ codes (M=64, C=256: the reference's "4-bit") plus a 128-token fp16 window.
@@ -7,9 +9,13 @@ A "step" = one decoded token: the PQ decode-attention hot path run for all 32 la
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--bs B] [--ctx T]
 
 Prints ONE JSON line (see the task contract).  `value` = tokens/s with everything resident in HBM (CUDA-graph replay of
-the 32 launches, CUDA events); `e2e` = tokens/s through the reference-facing cache API (DynamicPQCache.decoding) with
-HOST inputs/outputs copied inside the timed region; `roofline` = algorithmic bytes / measured kernel time against the
-measured HBM peak; `cpu_baseline` = the C oracle (OpenMP, all host cores) on a bounded sample.
+the 32 launches, CUDA events); `e2e` = tokens/s through the reference-facing cache API (DynamicPQCache, one CUDA graph per
+step: decode_step_graph) with HOST inputs/outputs copied inside the timed region; `roofline` = algorithmic bytes / measured
+kernel time against the measured HBM peak; `cpu_baseline` = the C oracle (OpenMP, all host cores) on a bounded sample.
+
+N > 1 (torchrun, one rank per GPU): the headline is sharded BY KV HEAD with no collective (north_star / SURVEY 8(e)): the
+global batch is 8 N sequences, rank g owns kv-heads [g*8/N, (g+1)*8/N) and their query heads, so the per-GPU work is that
+of N = 1 (weak scaling).  `extra.splitkv_128k` is the other partitioning (by sequence, batch 1, strong scaling).
 """
 import argparse
 import json
@@ -25,9 +31,10 @@ sys.path.insert(0, ROOT)
 LAYERS, NH, NH_K, D, M, C, LT = 32, 32, 8, 128, 64, 256, 128
 
 
-def algorithmic_bytes(bs, nk, r, nh=NH, nh_k=NH_K, d=D, m=M, c=C):
-    """codes once per KV head + fp16 window + both codebooks + q/o."""
-    return 2 * bs * nh_k * nk * m + 2 * bs * nh_k * r * d * 2 + 2 * m * c * (d // m) * 2 + 2 * bs * nh * d * 2
+def algorithmic_bytes(bs, nk, r, nh=NH, nh_k=NH_K, d=D, m=M, c=C, k_out=0, v_out=0):
+    """codes once per KV head + fp16 window + both codebooks + q/o (+ 3 bytes per outlier record)."""
+    return (2 * bs * nh_k * nk * m + 2 * bs * nh_k * r * d * 2 + 2 * m * c * (d // m) * 2 + 2 * bs * nh * d * 2
+            + 3 * (k_out + v_out) * bs * nh_k * nk)
 
 
 def measured_peaks():
@@ -82,19 +89,23 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(args, world):
+    return {"workload": f"llama31-8b-shapes_pq4bit_decode_attn_ctx{args.ctx}", "bs_per_gpu": args.bs, "global_batch": args.bs * world, "layers": LAYERS,
+            "nh": NH, "nh_k": NH_K, "d": D, "M": M, "C": C, "window": LT}
+
+
 # ------------------------------------------------------------------------------------------------ CPU arms
 
 
 def cpu_sample_inputs(nk, bs=1):
-    import numpy as np
     from oracle import pq_oracle as O
     return O.make_inputs(bs=bs, nh=NH, nh_k=NH_K, nk=nk, d=D, M=M, C=C, Lt=LT, seed=42)
 
 
-def cpu_baseline_port(nk, r):
-    """C oracle (oracle/pq_oracle.c, OpenMP) on ONE layer, bs=1; scaled to 32 layers."""
+def cpu_baseline_port(bs, nk, r):
+    """C oracle (oracle/pq_oracle.c, OpenMP) on ONE layer of the step at the bench's batch; scaled to 32 layers."""
     from oracle import c_oracle as CO
-    inp = cpu_sample_inputs(nk)
+    inp = cpu_sample_inputs(nk, bs)
     f32 = {k: (v.astype("float32") if v.dtype != "uint8" else v) for k, v in inp.items()}
     CO.pq_decode_attn(f32["q"], f32["kc"], f32["vc"], f32["kcent"], f32["vcent"], f32["kres"], f32["vres"], r)
     t0, n = time.perf_counter(), 0
@@ -102,44 +113,77 @@ def cpu_baseline_port(nk, r):
         CO.pq_decode_attn(f32["q"], f32["kc"], f32["vc"], f32["kcent"], f32["vcent"], f32["kres"], f32["vres"], r)
         n += 1
     per_layer = (time.perf_counter() - t0) / n
-    return {"value": 1.0 / (per_layer * LAYERS), "unit": "tokens/s", "cores": CO.num_threads(), "kind": "port",
-            "sample": f"1 of {LAYERS} layers, bs 1, ctx {nk + r}: {n} calls of oracle/pq_oracle.c, {per_layer*1e3:.2f} ms each, scaled x{LAYERS} layers"}
+    return {"value": bs / (per_layer * LAYERS), "unit": "tokens/s", "cores": CO.num_threads(), "kind": "port",
+            "sample": f"1 of {LAYERS} layers, bs {bs}, ctx {nk + r}: {n} calls of oracle/pq_oracle.c, {per_layer*1e3:.2f} ms each, scaled x{LAYERS} layers"}
+
+
+def _staged_reference():
+    """The reference's own scripts/utils/pq_utils.py (staged unmodified by oracle/stage_ref.py; pykeops stubbed — the decode path
+    below never touches it), or None."""
+    ref_py = os.path.join(ROOT, "oracle", "_ref", "ref_py")
+    if not os.path.exists(os.path.join(ref_py, "scripts", "utils", "pq_utils.py")):
+        return None
+    import types
+    mod, sub = types.ModuleType("pykeops"), types.ModuleType("pykeops.torch")
+    sub.LazyTensor = object
+    mod.torch = sub
+    sys.modules.setdefault("pykeops", mod)
+    sys.modules.setdefault("pykeops.torch", sub)
+    sys.path.insert(0, ref_py)
+    try:
+        import scripts.utils.pq_utils as ref
+        return ref
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(ref_py)
 
 
 def reference_arm(args):
-    """The reference's own CPU path for this op, restated with the same torch calls it makes: sa_decode_4d-style
-    gather of both code caches (pq_utils.py:501-540) + concat with the fp16 window + F.scaled_dot_product_attention
-    without mask (pq_utils.py:360-368), fp32 on all host threads.  One step = one layer of the 32-layer token on a
-    bounded batch (bs 1); tokens/s scaled to 32 layers."""
-    import numpy as np
+    """The reference's CPU implementation of this op on the box's host cores, SAME config as our arm (batch included): the
+    invariant the reference states for its kernel (pq_utils.py:360-368) evaluated with the reference's own sa_decode_4d
+    (pq_utils.py:501-540, loaded unmodified from the staged copy; the oracle's restatement if that is absent) +
+    F.scaled_dot_product_attention without mask, fp32, all host threads.  One step = ONE layer of the 32-layer token at the
+    bench's batch (a bounded sample: `ms_per_step` is that measured step); `value` = bs / (32 x step)."""
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    nk, r = args.ctx - LT, LT
-    inp = cpu_sample_inputs(nk)
+    bs, nk, r = args.bs, args.ctx - LT, LT
+    inp = cpu_sample_inputs(nk, bs)
     q = torch.from_numpy(inp["q"]).float()
-    kc, vc = torch.from_numpy(inp["kc"]).long(), torch.from_numpy(inp["vc"]).long()
+    kc, vc = torch.from_numpy(inp["kc"]), torch.from_numpy(inp["vc"])
     kcent, vcent = torch.from_numpy(inp["kcent"]).float(), torch.from_numpy(inp["vcent"]).float()
     kres, vres = torch.from_numpy(inp["kres"]).float(), torch.from_numpy(inp["vres"]).float()
-    ar = torch.arange(M)
+    ref = _staged_reference()
+    if ref is not None:
+        kind, decode = "reference", lambda codes, cent: ref.sa_decode_4d(codes.long(), cent)
+    else:
+        ar = torch.arange(M)
+        kind, decode = "port", lambda codes, cent: cent[ar, codes.long()].reshape(bs, NH_K, nk, D)
+    G = NH // NH_K
 
     def layer():
-        K = torch.cat([kcent[ar, kc].reshape(1, NH_K, nk, D), kres[:, :, :r]], 2).repeat_interleave(NH // NH_K, 1)
-        V = torch.cat([vcent[ar, vc].reshape(1, NH_K, nk, D), vres[:, :, :r]], 2).repeat_interleave(NH // NH_K, 1)
-        return torch.nn.functional.scaled_dot_product_attention(q, K, V)
+        K = torch.cat([decode(kc, kcent), kres[:, :, :r]], 2)
+        V = torch.cat([decode(vc, vcent), vres[:, :, :r]], 2)
+        # GQA without materialising repeat_kv: the G query heads of a KV head are G rows of one SDPA problem
+        o = torch.nn.functional.scaled_dot_product_attention(q.reshape(bs, NH_K, G, D), K, V)
+        return o.reshape(bs, NH, 1, D)
 
-    for _ in range(args.warmup):
+    for _ in range(max(1, min(args.warmup, 2))):
         layer()
+    steps = max(1, args.steps)          # exactly K measured steps (about 2 s each on 8 cores at bs 8)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         layer()
-    per_layer = (time.perf_counter() - t0) / args.steps
-    val = 1.0 / (per_layer * LAYERS)
-    line = {"metric": "pq_decode_attn_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_layer * LAYERS * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"llama31-8b-shapes_pq4bit_decode_attn_ctx{args.ctx}", "bs": 1, "layers": LAYERS},
-            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"each step = 1 of {LAYERS} layers at bs 1 (torch CPU gather + SDPA fp32), scaled x{LAYERS}"},
+    per_layer = (time.perf_counter() - t0) / steps
+    val = bs / (per_layer * LAYERS)
+    sample = (f"each step = 1 of {LAYERS} layers at bs {bs}, ctx {args.ctx} ({'reference sa_decode_4d' if kind == 'reference' else 'oracle restatement of sa_decode_4d'}"
+              f" + torch SDPA fp32 on {torch.get_num_threads()} threads): {per_layer*1e3:.1f} ms measured; tokens/s = bs / ({LAYERS} x step)")
+    cfg = workload_config(args, 1)
+    cfg.update({"layers_per_step": 1, "sharding": "host cores"})
+    line = {"metric": "pq_decode_attn_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": per_layer * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -147,61 +191,109 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------ GPU arm
 
 
-def build_layers(torch, bs, nk, device, n_layers):
+class Timer:
+    """CUDA events on the current stream + barrier / max over ranks (the contract's timing rule)."""
+
+    def __init__(self, torch, dist, world, device):
+        self.torch, self.dist, self.world, self.device = torch, dist, world, device
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, steps, sync_ranks=True):
+        """seconds for `steps` calls of fn (max over ranks when sync_ranks)."""
+        if sync_ranks:
+            self.barrier()
+        else:
+            self.torch.cuda.synchronize()
+        self.e0.record()
+        for _ in range(steps):
+            fn()
+        self.e1.record()
+        if sync_ranks:
+            self.barrier()
+        else:
+            self.torch.cuda.synchronize()
+        secs = self.e0.elapsed_time(self.e1) / 1e3
+        if sync_ranks and self.world > 1:
+            t = self.torch.tensor([secs], device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            secs = float(t.item())
+        return secs
+
+
+def capture(torch, fn, warm=1):
+    """Run fn on a side stream (first-use initialisation), then capture it into a CUDA graph."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(warm):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def build_layers(torch, bs, nh, nh_k, nk, device, n_layers, m=M, k_out=0, seed=42):
     g = torch.Generator(device=device)
-    g.manual_seed(42)
-    kcent = torch.randn(M, C, D // M, device=device, generator=g).half()
-    vcent = torch.randn(M, C, D // M, device=device, generator=g).half()
+    g.manual_seed(seed)
+    kcent = torch.randn(m, C, D // m, device=device, generator=g).half()
+    vcent = torch.randn(m, C, D // m, device=device, generator=g).half()
     layers = []
     for _ in range(n_layers):
         layers.append(dict(
-            kc=torch.randint(0, C, (bs, NH_K, nk, M), dtype=torch.uint8, device=device, generator=g),
-            vc=torch.randint(0, C, (bs, NH_K, nk, M), dtype=torch.uint8, device=device, generator=g),
-            kres=torch.randn(bs, NH_K, LT, D, device=device, generator=g).half(),
-            vres=torch.randn(bs, NH_K, LT, D, device=device, generator=g).half(),
-            q=torch.randn(bs, NH, 1, D, device=device, generator=g).half(),
-            out=torch.empty(bs, NH, 1, D, device=device, dtype=torch.float16)))
+            kc=torch.randint(0, C, (bs, nh_k, nk, m), dtype=torch.uint8, device=device, generator=g),
+            vc=torch.randint(0, C, (bs, nh_k, nk, m), dtype=torch.uint8, device=device, generator=g),
+            kres=torch.randn(bs, nh_k, LT, D, device=device, generator=g).half(),
+            vres=torch.randn(bs, nh_k, LT, D, device=device, generator=g).half(),
+            q=torch.randn(bs, nh, 1, D, device=device, generator=g).half(),
+            out=torch.empty(bs, nh, 1, D, device=device, dtype=torch.float16),
+            ko=(torch.randint(0, D, (bs, nh_k, nk, k_out), dtype=torch.uint8, device=device, generator=g),
+                (0.1 * torch.randn(bs, nh_k, nk, k_out, device=device, generator=g)).half()) if k_out else None))
     return kcent, vcent, layers
 
 
-def time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=0, k_out=0):
-    """Graph-replayed 32-layer step, inputs resident.  Returns (seconds for `steps` steps, launches).
-    k_out > 0: with a K-side outlier store of that many (dim, delta) records per coded token (extension)."""
-    kcent, vcent, layers = build_layers(torch, bs, nk, device, LAYERS)
-    ws = ops.attn_workspace(device, bs, NH, NH_K, D, ops.default_splits(bs, NH_K, nk))
-    for L_ in layers:
-        L_["ko"] = (torch.randint(0, D, (bs, NH_K, nk, k_out), dtype=torch.uint8, device=device),
-                    torch.randn(bs, NH_K, nk, k_out, device=device).half()) if k_out else None
+def resident_graph(torch, ops, bs, nh, nh_k, nk, r, device, impl=0, k_out=0, m=M, n_buffers=LAYERS, n_launch=LAYERS):
+    """CUDA graph of one n_launch-layer step over n_buffers distinct resident layer caches."""
+    kcent, vcent, layers = build_layers(torch, bs, nh, nh_k, nk, device, n_buffers, m=m, k_out=k_out)
+    ws = ops.attn_workspace(device, bs, nh, nh_k, D, ops.default_splits(bs, nh_k, nk))
 
     def step():
-        for L_ in layers:
+        for i in range(n_launch):
+            L_ = layers[i % n_buffers]
             ops.pq_decode_attn(L_["q"], L_["kc"], L_["vc"], kcent, vcent, L_["kres"], L_["vres"], r, out=L_["out"], workspace=ws, impl=impl,
                                k_outliers=L_["ko"])
 
-    s = torch.cuda.Stream(device=device)
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        step()
-    torch.cuda.current_stream().wait_stream(s)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        step()
-    for _ in range(warmup):
-        graph.replay()
-    return graph, layers, (kcent, vcent)
+    return capture(torch, step), layers, (kcent, vcent)
+
+
+def ncu_traffic(bs):
+    """DRAM bytes per launch of the headline kernel from this round's `ncu --set full` capture (profiles/r02_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum), or None — a profiler number cannot be taken inside a timed run."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(p):
+        j = json.load(open(p)).get(f"attn_fast_bs{bs}")
+        if j:
+            return j["dram_bytes_read"] + j["dram_bytes_write"]
+    return None
 
 
 def encode_rate(torch, ops, device):
-    """PQ encode throughput on Llama-3.1-8B prefill shapes: K of one layer = 8 kv-heads x 32768 tokens, for the encoder AUTO
-    picks (the exact candidate-grid encoder for d/M = 2) and for the tcgen05 distance encoder."""
+    """PQ encode throughput on Llama-3.1-8B prefill shapes (K of one layer = 8 kv-heads x 32768 tokens): the encoder AUTO picks
+    for M=64 (candidate grid) and M=32, and the tcgen05 distance encoder for M=64."""
     from million_b200 import _lib as L
     n = 32768
-    X = torch.randn(1, NH_K, n, D, device=device).half()
-    cent = torch.randn(M, C, D // M, device=device).half().float().contiguous()
-    codes = torch.empty(1, NH_K, n, M, dtype=torch.uint8, device=device)
     out = {}
-    for name, impl in (("auto_grid", L.IMPL_AUTO), ("tcgen05", L.IMPL_FAST)):
+    for name, m, impl in (("M64_auto_grid", 64, L.IMPL_AUTO), ("M64_tcgen05", 64, L.IMPL_FAST), ("M32_auto", 32, L.IMPL_AUTO)):
+        X = torch.randn(1, NH_K, n, D, device=device).half()
+        cent = torch.randn(m, C, D // m, device=device).half().float().contiguous()
+        codes = torch.empty(1, NH_K, n, m, dtype=torch.uint8, device=device)
         for _ in range(3):
             ops.pq_encode_into(X, cent, codes, impl=impl)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -213,18 +305,196 @@ def encode_rate(torch, ops, device):
         vec_per_s = NH_K * n / (ms * 1e-3)
         out[name] = {"M_head_vectors_per_s": vec_per_s / 1e6, "Mtok_per_s_32_layers_K_and_V": vec_per_s / (2 * NH_K * LAYERS) / 1e6,
                      "brute_force_equivalent_TFLOPs": vec_per_s * 2 * D * C / 1e12, "ms_per_layer_K_32k": ms,
-                     "hbm_GBps_input_plus_codes": vec_per_s * (2 * D + M) / 1e9}
+                     "hbm_GBps_input_plus_codes": vec_per_s * (2 * D + m) / 1e9}
     return out
 
 
-def ncu_traffic(bs):
-    """dram bytes per launch from the committed ncu capture of this kernel (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        j = json.load(open(p)).get(f"attn_fast_bs{bs}")
-        if j:
-            return j["dram_bytes_read"] + j["dram_bytes_write"]
-    return None
+def reference_cuda_kernel(torch, device, nk, r, ours_us):
+    """The REFERENCE's own decode kernels (flash_decoding_split / residual / reduce, Kernel.cuh), compiled for sm_100a from the
+    reference sources by oracle/build_ref.sh, timed as Interface.cu:49-118 runs them (at::matmul LUT + 3 launches + memset),
+    Llama-3.1-8B shapes, batch 1 (its registry hard-wires bs = 1), fp16, Ns = 32.  A comparator, not the product path."""
+    import ctypes
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_kernels.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libref_kernels.so not built (oracle/build_ref.sh needs /root/reference)"}
+    lib = ctypes.CDLL(so)
+    Ns, n_buf = 32, 8
+    kcent, vcent, layers = build_layers(torch, 1, NH, NH_K, nk, device, n_buf)
+    pout = torch.empty(1, NH, Ns + 1, D, dtype=torch.float16, device=device)
+    plse = torch.empty(1, NH, Ns + 1, dtype=torch.float16, device=device)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    kT = kcent.transpose(1, 2)
+    i = [0]
+
+    def call():
+        L_ = layers[i[0] % n_buf]; i[0] += 1
+        lut = torch.matmul(L_["q"].reshape(1, NH, 1, M, D // M).transpose(2, 3), kT).contiguous()      # Interface.cu:49-50
+        rc = lib.ref_flash_decoding_f16u8_Lt128d128M64C256(Ns, p(lut), p(L_["kc"]), p(L_["vc"]), p(vcent), p(L_["q"]), p(L_["kres"]), p(L_["vres"]), r,
+                                                           p(pout), p(plse), p(L_["out"]), 1, NH, NH_K, nk,
+                                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+
+    for _ in range(8):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    n = 64
+    for _ in range(n):
+        call()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / n * 1e3
+    return {"us_per_layer": us, "ours_us_per_layer": ours_us, "ours_speedup": us / ours_us if ours_us else None,
+            "config": f"llama31-8b shapes, ctx {nk + r}, bs 1, f16, Ns 32, eager launches incl. at::matmul LUT",
+            "source": "scripts/modeldb/bindings/Kernel.cuh + Interface.cu:49-118, nvcc -arch sm_100a --use_fast_math (setup.py:72)"}
+
+
+def splitkv_128k(torch, dist, ops, T, world, rank, device, peak, steps):
+    """BASELINE config 4: Llama-3.1-8B shapes, 128K context, batch 1, split-KV (by sequence) over the ranks — strong scaling.
+    Every rank runs the attention kernel with MILLION_ATTN_PARTIAL_ONLY on its page-aligned token range; the (o, m, l) states
+    are exchanged and merged by million_splitkv_push_merge (NVLink peer stores + flags; one launch; the whole 32-layer step is
+    one CUDA graph).  The 1-GPU time is measured in the same run on rank 0."""
+    from million_b200 import sharding
+    ctx = 131072
+    nk, r = ctx - LT, LT
+    n_buf = LAYERS
+    g = torch.Generator(device=device); g.manual_seed(1234)      # same seed on every rank -> identical tensors
+    kcent = torch.randn(M, C, 2, device=device, generator=g).half()
+    vcent = torch.randn(M, C, 2, device=device, generator=g).half()
+    q = torch.randn(1, NH, 1, D, device=device, generator=g).half()
+    kres = torch.randn(1, NH_K, LT, D, device=device, generator=g).half()
+    vres = torch.randn(1, NH_K, LT, D, device=device, generator=g).half()
+    kc_full = torch.randint(0, C, (1, NH_K, nk, M), dtype=torch.uint8, device=device, generator=g)
+    vc_full = torch.randint(0, C, (1, NH_K, nk, M), dtype=torch.uint8, device=device, generator=g)
+    s, e = sharding.split_kv_ranges(nk, world)[rank]
+    r_local = r if rank == world - 1 else 0
+    res = {"ctx": ctx, "bs": 1, "layers": LAYERS, "scaling": "strong", "tokens_per_rank": e - s}
+    single = ops.pq_decode_attn(q, kc_full, vc_full, kcent, vcent, kres, vres, r)
+    alg = algorithmic_bytes(1, nk, r)
+    if world > 1:
+        peer = sharding.SplitKVPeerGroup(NH, D, torch.float16)
+        merged = peer.decode_attn(q, kc_full[:, :, s:e].contiguous(), vc_full[:, :, s:e].contiguous(), kcent, vcent, kres, vres, r_local).clone()
+        err = torch.tensor([(merged.float() - single.float()).abs().max().item()], device=device)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        res["max_abs_merged_minus_single_gpu"] = float(err.item())
+        local = [(torch.randint(0, C, (1, NH_K, e - s, M), dtype=torch.uint8, device=device), torch.randint(0, C, (1, NH_K, e - s, M), dtype=torch.uint8, device=device))
+                 for _ in range(n_buf)]
+        out = torch.empty(1, NH, 1, D, dtype=torch.float16, device=device)
+
+        def step():
+            for k_, v_ in local:
+                peer.decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, out=out)
+
+        graph = capture(torch, step, warm=2)
+        for _ in range(3):
+            graph.replay()
+        secs = T.run(graph.replay, steps)
+        timed_out = torch.tensor([1.0 if peer.timed_out() else 0.0], device=device)
+        dist.all_reduce(timed_out, op=dist.ReduceOp.MAX)
+        res.update({"ms_per_token": secs / steps * 1e3, "tokens_per_s": steps / secs, "us_per_layer": secs / steps / LAYERS * 1e6,
+                    "frac_of_hbm_roofline_per_gpu": alg / world / (secs / steps / LAYERS) / 1e9 / peak,
+                    "exchange": "million_splitkv_push_merge (NVLink peer stores + flags), 2 launches per layer, one CUDA graph per step",
+                    "exchange_timed_out": bool(timed_out.item())})
+        del graph, local, peer
+    # the 1-GPU number of the same run (rank 0; the others wait at the barrier)
+    one = None
+    if rank == 0:
+        full = [(kc_full, vc_full)] + [(torch.randint(0, C, (1, NH_K, nk, M), dtype=torch.uint8, device=device), torch.randint(0, C, (1, NH_K, nk, M), dtype=torch.uint8, device=device))
+                                       for _ in range(n_buf - 1)]
+        out1 = torch.empty(1, NH, 1, D, dtype=torch.float16, device=device)
+
+        def step1():
+            for k_, v_ in full:
+                ops.pq_decode_attn(q, k_, v_, kcent, vcent, kres, vres, r, out=out1)
+
+        g1 = capture(torch, step1)
+        for _ in range(3):
+            g1.replay()
+        one = T.run(g1.replay, steps, sync_ranks=False) / steps
+        del g1, full
+    if world > 1:
+        t = torch.tensor([one or 0.0], device=device)
+        dist.broadcast(t, 0)
+        one = float(t.item())
+    res["one_gpu"] = {"ms_per_token": one * 1e3, "tokens_per_s": 1.0 / one, "us_per_layer": one / LAYERS * 1e6,
+                      "frac_of_hbm_roofline": alg / (one / LAYERS) / 1e9 / peak}
+    if world > 1:
+        res["speedup_vs_one_gpu"] = one / (res["ms_per_token"] / 1e3)
+    else:
+        res.update({"ms_per_token": one * 1e3, "tokens_per_s": 1.0 / one, "us_per_layer": one / LAYERS * 1e6})
+    torch.cuda.empty_cache()
+    return res
+
+
+def kvhead_7b(torch, ops, T, world, rank, device, peak, steps):
+    """BASELINE config 5: Llama-2-7B shapes (MHA, 32 heads), 64K context, batch 16, KV heads sharded over the ranks (no
+    collective), 4-bit (M=64) and 2-bit (M=32) PQ with a K-side outlier store of 2 records per token.  Each rank times its own
+    32/N heads; the job's tokens/s is 16 / (max over ranks of the 32-layer step).  Layer caches larger than the memory budget are
+    cycled over fewer distinct buffers (each still many times the L2)."""
+    ctx, bs, heads = 65536, 16, 32
+    nk, r = ctx - LT, LT
+    if heads % world:
+        return {"unavailable": f"32 heads do not divide over {world} ranks"}
+    nh = heads // world
+    out = {"ctx": ctx, "bs": bs, "heads_per_rank": nh, "layers": LAYERS, "sharding": f"by KV head: {nh} of 32 MHA heads per rank, no collective"}
+    for name, m, k_out in (("M64_4bit_kout2", 64, 2), ("M32_2bit_kout2", 32, 2), ("M64_4bit_plain", 64, 0)):
+        per_layer = 2 * bs * nh * nk * m + 3 * k_out * bs * nh * nk
+        n_buf = max(2, min(LAYERS, int(12e9 // per_layer)))
+        graph, layers, cents = resident_graph(torch, ops, bs, nh, nh, nk, r, device, k_out=k_out, m=m, n_buffers=n_buf)
+        for _ in range(2):
+            graph.replay()
+        secs = T.run(graph.replay, steps)
+        alg = algorithmic_bytes(bs, nk, r, nh=nh, nh_k=nh, m=m, k_out=k_out)
+        out[name] = {"tokens_per_s_aggregate": bs * steps / secs, "ms_per_token_step": secs / steps * 1e3, "us_per_layer_per_rank": secs / steps / LAYERS * 1e6,
+                     "algorithmic_bytes_per_launch_per_rank": alg, "frac_of_hbm_roofline_per_gpu": alg / (secs / steps / LAYERS) / 1e9 / peak,
+                     "distinct_layer_buffers": n_buf}
+        del graph, layers, cents
+        torch.cuda.empty_cache()
+    return out
+
+
+def paged_prefill_async(torch, device):
+    """BASELINE config 3: Llama-3.1-8B shapes, PagedPQCache: the quantize-and-page part of a 32K prefill (32 layers), then decode
+    with the retiring block quantized synchronously (the reference, paged_pq_utils.py:357-360) vs asynchronously on a side stream."""
+    from million_b200.paged_pq_utils import PagedPQCache
+    from million_b200.pq_utils import Singleton
+    T0, steps = 32768, 136
+    g = torch.Generator(device=device); g.manual_seed(0)
+    ck, cv = torch.randn(M, C, 2, device=device, generator=g).half(), torch.randn(M, C, 2, device=device, generator=g).half()
+    k0 = torch.randn(1, NH_K, T0, D, device=device, generator=g).half()
+    v0 = torch.randn(1, NH_K, T0, D, device=device, generator=g).half()
+    qs = torch.randn(LAYERS, 1, NH, 1, D, device=device, generator=g).half()
+    ks = torch.randn(LAYERS, 1, NH_K, 1, D, device=device, generator=g).half()
+    vs = torch.randn(LAYERS, 1, NH_K, 1, D, device=device, generator=g).half()
+    res = {}
+    for mode, async_flush in (("sync_flush", False), ("async_flush", True)):
+        Singleton.clear_instance()
+        cache = PagedPQCache(bs=1, nh=NH, num_key_value_heads=NH_K, M=M, layer_num=LAYERS, d=D, scalar_t=torch.float16, async_flush=async_flush, device=device)
+        cache.set_cent(ck, cv)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for l in range(LAYERS):
+            cache._encode_append(k0, v0, l)           # the quantize-and-page part of prefill() (its SDPA is library code)
+        e1.record(); torch.cuda.synchronize()
+        prefill_ms = e0.elapsed_time(e1)
+        for _ in range(70):                            # warm-up across the first flush
+            for l in range(LAYERS):
+                cache.decoding_with_pages(qs[l], ks[l], vs[l], l)
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for s_ in range(steps):
+            for l in range(LAYERS):
+                cache.decoding_with_pages(qs[l], ks[l], vs[l], l)
+            evs[s_ + 1].record()
+        torch.cuda.synchronize()
+        ts = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        res[mode] = {"prefill_encode_ms_32k_x_32_layers": prefill_ms, "prefill_Mtok_per_s": T0 / prefill_ms / 1e3,
+                     "decode_step_ms_mean": sum(ts) / steps, "decode_step_ms_p50": ts[steps // 2], "decode_step_ms_max": ts[-1],
+                     "flushes_in_window": steps // 64}
+        del cache
+        Singleton.clear_instance()
+        torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -237,6 +507,7 @@ def main():
     ap.add_argument("--ctx", type=int, default=32768)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -272,127 +543,126 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    if NH_K % world:
+        raise SystemExit(f"KV-head sharding needs {NH_K} % n_gpus == 0")
 
-    bs, nk, r = args.bs, args.ctx - LT, LT
+    # KV-head sharding of a global batch bs * world (weak scaling): this rank's slice of the problem
+    bs_g, nh_l, nhk_l = args.bs * world, NH // world, NH_K // world
+    nk, r = args.ctx - LT, LT
     steps, warmup = args.steps, max(args.warmup, 3)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    T = Timer(torch, dist, world, device)
+    peak, peak_src = measured_peaks()
 
     # ---- resident-inputs number (value) + roofline
-    graph, layers, cents = time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=args.kernel)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    graph, layers, cents = resident_graph(torch, ops, bs_g, nh_l, nhk_l, nk, r, device, impl=args.kernel)
+    for _ in range(warmup):
+        graph.replay()
     with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(steps):
-            graph.replay()
-        e1.record()
-        barrier()
-    secs = e0.elapsed_time(e1) / 1e3
-    if world > 1:
-        t = torch.tensor([secs], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs = float(t.item())
+        secs = T.run(graph.replay, steps)
     launches = LAYERS * steps
     per_launch = secs / launches
-    alg = algorithmic_bytes(bs, nk, r)
-    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes(bs_g, nk, r, nh=nh_l, nh_k=nhk_l)          # per rank = the N = 1 figure
     achieved = alg / per_launch / 1e9
-    value = world * bs * steps / secs
+    value = bs_g * steps / secs
 
-    # ---- batch-1 latency shape of the same config (reported alongside, not the headline)
     extra = {}
-    if rank == 0 and bs != 1:
-        g1, l1, c1 = time_resident(torch, ops, 1, nk, r, steps, warmup, device, impl=args.kernel)
-        torch.cuda.synchronize(); e0.record()
-        for _ in range(steps):
-            g1.replay()
-        e1.record(); torch.cuda.synchronize()
-        s1 = e0.elapsed_time(e1) / 1e3
-        a1 = algorithmic_bytes(1, nk, r) / (s1 / launches) / 1e9
-        extra["bs1"] = {"tokens_per_s": steps / s1, "us_per_layer": s1 / launches * 1e6, "achieved_GBps": a1, "frac": a1 / peak}
-        del g1, l1, c1
-        # the same step with a K-side outlier store (2 records per coded token and KV head: +6 bytes on 128)
-        g2, l2, c2 = time_resident(torch, ops, bs, nk, r, steps, warmup, device, impl=args.kernel, k_out=2)
-        torch.cuda.synchronize(); e0.record()
-        for _ in range(steps):
-            g2.replay()
-        e1.record(); torch.cuda.synchronize()
-        s2 = e0.elapsed_time(e1) / 1e3
-        alg2 = alg + 3 * 2 * bs * NH_K * nk
-        extra["k_outliers_2"] = {"tokens_per_s": bs * steps / s2, "us_per_layer": s2 / launches * 1e6,
-                                 "achieved_GBps": alg2 / (s2 / launches) / 1e9, "frac": alg2 / (s2 / launches) / 1e9 / peak}
-        del g2, l2, c2
-        try:
-            extra["encode"] = encode_rate(torch, ops, device)
-        except Exception as e:
-            extra["encode"] = {"error": repr(e)}
-    barrier()
 
-    # ---- end-to-end through the reference-facing API with HOST buffers
+    def guarded(name, fn):
+        try:
+            extra[name] = fn()
+        except Exception as e:    # an extra must never hide the headline (deterministic failures hit every rank at the same point)
+            extra[name] = {"error": repr(e)[:300]}
+
+    if not args.no_extras:
+        if rank == 0:
+            def bs1():
+                g1, l1, c1 = resident_graph(torch, ops, 1, NH, NH_K, nk, r, device, impl=args.kernel)
+                for _ in range(warmup):
+                    g1.replay()
+                s1 = T.run(g1.replay, steps, sync_ranks=False)
+                a1 = algorithmic_bytes(1, nk, r) / (s1 / launches) / 1e9
+                return {"tokens_per_s": steps / s1, "us_per_layer": s1 / launches * 1e6, "achieved_GBps": a1, "frac": a1 / peak}
+            guarded("bs1", bs1)
+
+            def kout2():
+                # the same step with a K-side outlier store (2 records per coded token and KV head: +6 bytes on 128)
+                g2, l2, c2 = resident_graph(torch, ops, args.bs, NH, NH_K, nk, r, device, impl=args.kernel, k_out=2)
+                for _ in range(warmup):
+                    g2.replay()
+                s2 = T.run(g2.replay, steps, sync_ranks=False)
+                alg2 = algorithmic_bytes(args.bs, nk, r, k_out=2)
+                return {"tokens_per_s": args.bs * steps / s2, "us_per_layer": s2 / launches * 1e6,
+                        "achieved_GBps": alg2 / (s2 / launches) / 1e9, "frac": alg2 / (s2 / launches) / 1e9 / peak}
+            guarded("k_outliers_2", kout2)
+            guarded("encode", lambda: encode_rate(torch, ops, device))
+            guarded("reference_cuda_kernel", lambda: reference_cuda_kernel(torch, device, nk, r, extra.get("bs1", {}).get("us_per_layer")))
+            guarded("paged_prefill_32k_async_flush", lambda: paged_prefill_async(torch, device))
+        T.barrier()
+
+    # ---- end-to-end through the reference-facing API with HOST buffers: one CUDA graph per step (decode_step_graph)
     del graph
     Singleton.clear_instance()
-    cache = DynamicPQCache(bs=bs, nh=NH, num_key_value_heads=NH_K, M=M, layer_num=LAYERS, d=D, scalar_t=torch.float16, device=device)
+    cache = DynamicPQCache(bs=bs_g, nh=nh_l, num_key_value_heads=nhk_l, M=M, layer_num=LAYERS, d=D, scalar_t=torch.float16, device=device)
     cache.set_cent(*cents)
     for li, L_ in enumerate(layers):              # adopt the resident code caches as the prefilled state
         cache._k[li].buf, cache._k[li].cap, cache._k[li].len = L_["kc"], nk, nk
         cache._v[li].buf, cache._v[li].cap, cache._v[li].len = L_["vc"], nk, nk
         cache.seen_tokens[li] = nk
-    e2e_steps = min(steps, LT - 1)
-    hq = torch.randn(LAYERS, bs, NH, 1, D).half().pin_memory()
-    hk = torch.randn(LAYERS, bs, NH_K, 1, D).half().pin_memory()
-    hv = torch.randn(LAYERS, bs, NH_K, 1, D).half().pin_memory()
-    ho = torch.empty(LAYERS, bs, NH, 1, D, dtype=torch.float16).pin_memory()
+    e2e_warm = 3
+    e2e_steps = max(1, min(steps, LT - 1 - e2e_warm))
+    hq = torch.randn(LAYERS, bs_g, nh_l, 1, D).half().pin_memory()
+    hk = torch.randn(LAYERS, bs_g, nhk_l, 1, D).half().pin_memory()
+    hv = torch.randn(LAYERS, bs_g, nhk_l, 1, D).half().pin_memory()
+    ho = torch.empty(LAYERS, bs_g, nh_l, 1, D, dtype=torch.float16).pin_memory()
     dq, dk, dv = (torch.empty_like(x, device=device) for x in (hq, hk, hv))
-    do = torch.empty(LAYERS, bs, NH, 1, D, dtype=torch.float16, device=device)
+    do = torch.empty(LAYERS, bs_g, nh_l, 1, D, dtype=torch.float16, device=device)
+    stepper = cache.decode_step_graph(dq, dk, dv, do)
 
     def e2e_step():
         dq.copy_(hq, non_blocking=True); dk.copy_(hk, non_blocking=True); dv.copy_(hv, non_blocking=True)
-        for li in range(LAYERS):
-            do[li] = cache.decoding(dq[li], dk[li], dv[li], li)
+        stepper.step()
         ho.copy_(do, non_blocking=True)
 
-    for _ in range(3):
+    for _ in range(e2e_warm):
         e2e_step()
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps - 3):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_secs = e0.elapsed_time(e1) / 1e3
-    if world > 1:
-        t = torch.tensor([e2e_secs], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_secs = float(t.item())
-    e2e_val = world * bs * (e2e_steps - 3) / e2e_secs
+    e2e_secs = T.run(e2e_step, e2e_steps)
+    e2e_val = bs_g * e2e_steps / e2e_secs
     h2d = hq.numel() * 2 + hk.numel() * 2 + hv.numel() * 2
     d2h = ho.numel() * 2
+    del stepper, cache, layers
+    Singleton.clear_instance()
+    torch.cuda.empty_cache()
+
+    # ---- the other two north_star configurations, at every N
+    if not args.no_extras:
+        ext_steps = max(5, min(steps, 20))
+        guarded("splitkv_128k", lambda: splitkv_128k(torch, dist, ops, T, world, rank, device, peak, ext_steps))
+        guarded("kvhead_7b_64k_bs16", lambda: kvhead_7b(torch, ops, T, world, rank, device, peak, max(3, min(steps, 6))))
 
     if rank == 0:
+        cfg = workload_config(args, world)
+        cfg.update({"sharding": (f"by KV head, no collective: rank g owns kv-heads [g*{nhk_l}, (g+1)*{nhk_l}) and their {nh_l} query heads of a "
+                                 f"global batch of {bs_g} sequences" if world > 1 else "single GPU"),
+                    "l2": f"inputs larger than L2: {LAYERS} layer caches, {LAYERS * alg / 1e9:.2f} GB touched per step per GPU", "kernel": args.kernel})
         line = {
             "metric": "pq_decode_attn_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-            "data": "synthetic",
-            "config": {"workload": f"llama31-8b-shapes_pq4bit_decode_attn_ctx{args.ctx}", "bs_per_gpu": bs, "layers": LAYERS, "nh": NH, "nh_k": NH_K,
-                       "d": D, "M": M, "C": C, "window": r, "sharding": "independent sequences per rank (no collective)" if world > 1 else "single GPU",
-                       "l2": f"inputs larger than L2: {LAYERS} layer caches, {LAYERS * alg / 1e9:.2f} GB touched per step", "kernel": args.kernel},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(bs),
+            "data": "synthetic", "config": cfg,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.bs),
+                         "traffic_source": "ncu --set full capture of this launch, profiles/r02_traffic.json (null if absent)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "us_per_launch": per_launch * 1e6},
-            "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "DynamicPQCache.decoding x 32 layers, pinned host q/k/v in, host out"},
+            "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_secs / e2e_steps * 1e3,
+                    "api": "DynamicPQCache.decode_step_graph: pinned host q/k/v -> device, one CUDA graph (32 fused append+attention launches), device -> host out"},
             "gpu_launches": launches, "clocks": clk.summary(), "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline_port(nk, r)
+                line["cpu_baseline"] = cpu_baseline_port(args.bs, nk, r)
             except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MILLION_ABI_VERSION 6
+#define MILLION_ABI_VERSION 7
 
 typedef void* million_stream_t; /* cudaStream_t */
 
@@ -62,7 +62,7 @@ enum million_v_layout {
 
 /* which implementation to run; AUTO picks the fastest one that supports the shape */
 enum million_impl {
-    MILLION_IMPL_AUTO = 0,
+    MILLION_IMPL_AUTO = 0,    /* encode: expects the tables of million_pq_encoder_auto_prepare in `prepared_encoder` */
     MILLION_IMPL_GENERIC = 1, /* plain SIMT kernels, every shape */
     MILLION_IMPL_FAST = 2,    /* decode: conflict-free shared-memory LUT gathers (attn_fast.cu); encode: tcgen05 distances */
     MILLION_IMPL_GRID = 3     /* encode only, d/M = 2: exact candidate-grid search (encode_grid.cu); `prepared_encoder` must then
@@ -100,6 +100,12 @@ int million_pq_encoder_prepare(const float* cent, int x_dtype, int d, int M, int
  * Pass the buffer as `prepared_encoder` together with impl = MILLION_IMPL_GRID. */
 int64_t million_pq_encoder_grid_prepared_bytes(int d, int M, int C);
 int million_pq_encoder_grid_prepare(const float* cent, int d, int M, int C, void* prepared, million_stream_t stream);
+
+/* The tables MILLION_IMPL_AUTO wants in `prepared_encoder` for a shape: the candidate grid where it applies (d = 2M, C <= 256,
+ * one-byte codes), else the tensor-core tiles (same return codes as million_pq_encoder_prepare).  A host that passes these with
+ * impl = AUTO gets the fastest exact encoder without knowing which one that is; NULL runs the exact CUDA-core encoder. */
+int64_t million_pq_encoder_auto_prepared_bytes(int d, int M, int C);
+int million_pq_encoder_auto_prepare(const float* cent, int x_dtype, int d, int M, int C, void* prepared, million_stream_t stream);
 
 int million_pq_encode(const void* x, int x_dtype, int64_t x_head_stride,
                       const float* cent, const void* prepared_encoder /* may be NULL */,
@@ -218,6 +224,18 @@ typedef struct million_attn_params {
      * million_splitkv_state_bytes() block prepared once by million_splitkv_state_init.  EXPERIMENTAL: compiled only with
      * -DMILLION_FUSED_SPLITKV (slower than the separate exchange launch so far); other builds return MILLION_ERR_UNSUPPORTED. */
     void* p2p_state;
+
+    /* Window append fused into the attention launch (pq_utils.py:304-311 followed by :313-327, one launch instead of a copy
+     * kernel + the attention): k_new / v_new (bs, nh_k, d) io_dtype are the key/value of the token being decoded.  The kernel
+     * stores them into row r-1 of k_res / v_res and attends over them, so `r` COUNTS the new token.  NULL = the caller has
+     * appended already (million_window_append). */
+    const void* k_new;
+    const void* v_new;
+    /* Device-resident window length, for CUDA-graph replay of a decode step (the reference passes r by value,
+     * pq_utils.py:92): when non-NULL the kernel uses r = min(*r_dev + r, res_len), read at kernel start, so a captured
+     * launch with k_new/v_new and r = 1 means "append at row *r_dev, attend over *r_dev + 1 rows".  Bump the counter after the
+     * last layer of a step with million_counter_add.  Host-side checks on r then apply to the offset only. */
+    const int32_t* r_dev;
 } million_attn_params;
 
 #define MILLION_MAX_OUTLIERS 8
@@ -262,6 +280,9 @@ int million_splitkv_push_merge(const float* local_partial, void* const* peer_bas
 int million_window_append(void* k_win, void* v_win, int64_t win_head_stride,
                           const void* k_src, const void* v_src, int64_t src_head_stride,
                           int n_heads, int r0, int n, int d, int dtype, million_stream_t stream);
+
+/* ctr[i] += delta for i < n (device int32 counters, e.g. the r_dev of million_attn_params): one tiny launch, graph capturable. */
+int million_counter_add(int32_t* ctr, int n, int delta, million_stream_t stream);
 
 /* window[:, 0:rem, :] = window[:, shift:shift+rem, :] (paged flush, paged_pq_utils.py:186-199) */
 int million_window_shift(void* k_win, void* v_win, int64_t win_head_stride, int n_heads, int shift, int rem,

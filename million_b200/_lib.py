@@ -15,7 +15,7 @@ V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_FAST, IMPL_GRID = 0, 1, 2, 3
 ATTN_PARTIAL_ONLY = 1
 ATTN_FUSED_SPLITKV = 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
 
@@ -42,6 +42,7 @@ class AttnParams(ctypes.Structure):
         ("k_out_idx", c_vp), ("k_out_val", c_vp), ("k_out_head_stride", c_i64),
         ("v_out_idx", c_vp), ("v_out_val", c_vp), ("v_out_head_stride", c_i64),
         ("p2p_state", c_vp),
+        ("k_new", c_vp), ("v_new", c_vp), ("r_dev", c_vp),
     ]
 
 
@@ -54,6 +55,8 @@ SIGNATURES = {
     "million_pq_encoder_prepare": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "million_pq_encoder_grid_prepared_bytes": (c_i64, [ctypes.c_int] * 3),
     "million_pq_encoder_grid_prepare": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "million_pq_encoder_auto_prepared_bytes": (c_i64, [ctypes.c_int] * 3),
+    "million_pq_encoder_auto_prepare": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "million_pq_encode": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, ctypes.c_int, c_i64, c_i64, c_i64, c_i64,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "million_pq_encode_paged": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_i64,
@@ -76,6 +79,7 @@ SIGNATURES = {
     "million_splitkv_push_merge": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp]),
     "million_window_append": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, c_vp]),
+    "million_counter_add": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
     "million_window_shift": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, c_vp]),
 }

@@ -34,10 +34,25 @@ struct AttnArgs {
     int k_out, v_out;
     const uint8_t* ko_idx; const void* ko_val; int64_t ko_head_stride;
     const uint8_t* vo_idx; const void* vo_val; int64_t vo_head_stride;
-    int dbg_mode;                     // hidden ablation switch (million_debug_set_mode): bit 0 skips QK gathers, bit 1 skips PV
+    // fused window append: the new token's key/value (bs, nh_k, d), stored into window row r-1 by the CTA that owns that row
+    const void* k_new; const void* v_new;
+    const int* r_dev;                 // device-resident window length: r = min(*r_dev + r, res_len) (graph replay), or nullptr
+#ifdef MILLION_DEBUG
+    int dbg_mode;                     // ablation switch (million_debug_set_mode): bit 0 skips QK gathers, bit 1 skips PV, bit 2 tile loads
     unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 64 words per CTA, see dbg_stamp
+#endif
 };
 
+// window rows valid for this launch (see million_attn_params.r_dev)
+__device__ __forceinline__ int window_rows(const AttnArgs& a) {
+    if (a.r_dev == nullptr) return a.r;
+    const int r = __ldg(a.r_dev) + a.r;
+    return r < a.res_len ? r : a.res_len;
+}
+
+// Debug instrumentation exists only in -DMILLION_DEBUG builds (tools/attn_phases.py, tools/ablate.py): product builds carry
+// neither the globals nor the run-time branches.
+#ifdef MILLION_DEBUG
 // 64 words per CTA: raw globaltimer stamps [piece 0..3][slot 0..15] (stores only: a stamp must not wait on memory)
 __device__ __forceinline__ void dbg_stamp(unsigned long long* dbg_timing, int piece, int slot) {
     if (dbg_timing && threadIdx.x == 0 && piece < 4) {
@@ -47,6 +62,11 @@ __device__ __forceinline__ void dbg_stamp(unsigned long long* dbg_timing, int pi
     }
 }
 __device__ __forceinline__ void dbg_stamp(const AttnArgs& a, int slot, int piece = 0) { dbg_stamp(a.dbg_timing, piece, slot); }
+#define MILLION_DBG_MODE(a, bit) ((a).dbg_mode & (bit))
+#else
+__device__ __forceinline__ void dbg_stamp(const AttnArgs&, int, int = 0) {}
+#define MILLION_DBG_MODE(a, bit) 0
+#endif
 
 // tokens [begin, end) of split `s`
 __device__ __forceinline__ void split_range(const AttnArgs& a, int s, int& begin, int& end) {
@@ -98,10 +118,16 @@ struct MergeArgs {
     float* big;            // optional large shared staging buffer lent by the caller (dead tables), big_floats floats
     int big_floats;
     unsigned long long* bar;   // 8 bytes of shared memory for the mbarrier of the staged path
+#ifdef MILLION_DEBUG
     unsigned long long* dbg_timing;
     int dbg_piece;
+#endif
 };
+#ifdef MILLION_DEBUG
 __device__ __forceinline__ void dbg_stamp_m(const MergeArgs& a, int slot) { dbg_stamp(a.dbg_timing, a.dbg_piece, slot); }
+#else
+__device__ __forceinline__ void dbg_stamp_m(const MergeArgs&, int) {}
+#endif
 // Out of line on purpose: it runs once per group, and inlined into the attention kernels its registers and code perturb the
 // allocation and layout of their main loops (measured: +7 us per launch at batch 8 for the same loop rate).
 template <typename T>
@@ -341,9 +367,11 @@ template <typename T>
 __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, int n_parts, float* scr, float* big = nullptr, int big_floats = 0, unsigned long long* bar = nullptr, int dbg_piece = 0) {
     MergeArgs m;
     m.bar = bar;
-    m.dbg_piece = dbg_piece;
     m.big = big; m.big_floats = big_floats;
-    m.nh = a.nh; m.nh_k = a.nh_k; m.n_parts = a.n_parts; m.d = a.d; m.parts = a.parts; m.partial_out = a.partial_out; m.out = a.out; m.dbg_timing = a.dbg_timing;
+    m.nh = a.nh; m.nh_k = a.nh_k; m.n_parts = a.n_parts; m.d = a.d; m.parts = a.parts; m.partial_out = a.partial_out; m.out = a.out;
+#ifdef MILLION_DEBUG
+    m.dbg_piece = dbg_piece; m.dbg_timing = a.dbg_timing;
+#endif
     merge_group_impl<T>(m, b, hk, n_parts, scr);
 }
 

@@ -118,7 +118,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         for (int i = 0; i < 4; ++i) {
             const int chunk = lane + i * 32;            // 0..127: 32 tokens * 4 chunks of 16 B
             const int tok = tok0 + (chunk >> 2);
-            const int ok = (tile < n_tiles && tok < t1 && !(a.dbg_mode & 4)) ? 16 : 0;
+            const int ok = (tile < n_tiles && tok < t1 && !MILLION_DBG_MODE(a, 4)) ? 16 : 0;
             cp_async16(dst + chunk * 16, gbase + (int64_t)(ok ? tok : t0) * kRowBytes + (chunk & 3) * 16, ok);
         }
         cp_async_commit();
@@ -284,7 +284,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 uint32_t words[16];
 #pragma unroll
                 for (int w = 0; w < 16; ++w) words[w] = lds32(ksp, lane * kRowBytes + (((w + rot) & 15) << 2));   // word (w + rot) % 16 of my row
-                if (!(a.dbg_mode & 1))
+                if (!MILLION_DBG_MODE(a, 1))
 #pragma unroll
                     for (int w = 0; w < 16; ++w) qk_gathers(words[w], koff[w]);
             }
@@ -365,7 +365,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 // The half-warp takes tokens 4*jq + hw and 4*jq + hw + 2 of every group of four (their rows lie 16 banks away
                 // from the other half-warp's: conflict free); the p slots of those two tokens are adjacent (see p_slot), so ONE
                 // 16-byte broadcast load brings both.
-                if (!(a.dbg_mode & 2))
+                if (!MILLION_DBG_MODE(a, 2))
 #pragma unroll 2
                 for (int jq = 0; jq < kTile / 4; ++jq) {
                     const uint4 pk = lds128(pbuf_w, (4 * jq + 2 * hw) * 8);
@@ -451,7 +451,11 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
 #pragma unroll
     for (int g = 0; g < G; ++g) { wm[g] = -INFINITY; wl[g] = 0.f; wo[g][0] = wo[g][1] = wo[g][2] = wo[g][3] = 0.f; }
     {
-        const int w0 = (int)((long long)a.r * split / np), w1 = (int)((long long)a.r * (split + 1) / np);
+        const int rw = window_rows(a);
+        const int w0 = (int)((long long)rw * split / np), w1 = (int)((long long)rw * (split + 1) / np);
+        // fused append: window row rw-1 is the token being decoded; it is read from k_new / v_new and stored into the window here
+        // (by the one warp of the one split that owns that row), replacing the copy launch of pq_utils.py:304-311
+        const int t_new = a.k_new != nullptr ? rw - 1 : -1;
         if (w0 + warp < w1) {
             float qv[G][4];
 #pragma unroll
@@ -469,8 +473,17 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 for (int u = 0; u < kWinBatch; ++u) {
                     const int t = tb + u * kWarps;
                     const int64_t row = ((int64_t)hb * a.res_len + (t < w1 ? t : tb)) * 128 + 4 * lane;
-                    kr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
-                    vr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
+                    if (t == t_new) {
+                        kr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_new) + (int64_t)hb * 128 + 4 * lane));
+                        vr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_new) + (int64_t)hb * 128 + 4 * lane));
+                        if (sub == 0) {
+                            *reinterpret_cast<uint2*>(reinterpret_cast<T*>(const_cast<void*>(a.k_res)) + row) = kr[u];
+                            *reinterpret_cast<uint2*>(reinterpret_cast<T*>(const_cast<void*>(a.v_res)) + row) = vr[u];
+                        }
+                    } else {
+                        kr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
+                        vr[u] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
+                    }
                 }
                 float sg[kWinBatch][G];
 #pragma unroll
@@ -620,11 +633,8 @@ static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, 
     const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + (OUT ? 1024 : 256);
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= 2 * kWarps * 4 * 130 * sizeof(float), "stage + p area too small for the combine");
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
-    static bool configured = false;
-    if (!configured) {
-        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_kernel<T, G, VL, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemAttrOnce configured = {};
+    MILLION_CUDA_OK(ensure_dynamic_smem(configured, attn_fast_kernel<T, G, VL, OUT>, smem));
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
     if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
     attn_fast_kernel<T, G, VL, OUT><<<grid, block, smem, stream>>>(a, prepared, gsub);
@@ -657,7 +667,8 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
         MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");
     if (a.nk > 0 && a.v_layout == MILLION_V_ROWMAJOR && (((uintptr_t)a.v_codes | (uintptr_t)a.v_head_stride) & 15))
         MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");
-    if (a.r > 0 && (((uintptr_t)a.k_res | (uintptr_t)a.v_res) & 7)) MILLION_UNSUPPORTED("fast decode attention needs an 8-byte aligned window");
+    if ((a.r > 0 || a.r_dev) && (((uintptr_t)a.k_res | (uintptr_t)a.v_res | (uintptr_t)a.k_new | (uintptr_t)a.v_new) & 7))
+        MILLION_UNSUPPORTED("fast decode attention needs an 8-byte aligned window");
     if (probe_only) return MILLION_OK;
     const int G = Gfull >= 4 ? 4 : Gfull, gsub = Gfull >= 4 ? Gfull / 4 : 1;
     if (a.auto_splits && gsub == 1 && a.nk > 0) {

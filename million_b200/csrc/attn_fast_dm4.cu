@@ -345,7 +345,9 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
 #pragma unroll
     for (int g = 0; g < G; ++g) { wm[g] = -INFINITY; wl[g] = 0.f; wo[g][0] = wo[g][1] = wo[g][2] = wo[g][3] = 0.f; }
     {
-        const int w0 = (int)((long long)a.r * split / np), w1 = (int)((long long)a.r * (split + 1) / np);
+        const int rw = window_rows(a);
+        const int w0 = (int)((long long)rw * split / np), w1 = (int)((long long)rw * (split + 1) / np);
+        const int t_new = a.k_new != nullptr ? rw - 1 : -1;   // fused window append, as in attn_fast.cu
         if (w0 + warp < w1) {
             float qv[G][4];
 #pragma unroll
@@ -356,8 +358,18 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             }
             for (int t = w0 + warp; t < w1; t += kWarps) {
                 const int64_t row = ((int64_t)hb * a.res_len + t) * 128 + 4 * lane;
-                const uint2 kr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
-                const uint2 vr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
+                uint2 kr, vr;
+                if (t == t_new) {
+                    kr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_new) + (int64_t)hb * 128 + 4 * lane));
+                    vr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_new) + (int64_t)hb * 128 + 4 * lane));
+                    if (sub == 0) {
+                        *reinterpret_cast<uint2*>(reinterpret_cast<T*>(const_cast<void*>(a.k_res)) + row) = kr;
+                        *reinterpret_cast<uint2*>(reinterpret_cast<T*>(const_cast<void*>(a.v_res)) + row) = vr;
+                    }
+                } else {
+                    kr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.k_res) + row));
+                    vr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(a.v_res) + row));
+                }
                 const float2 k01 = io<T>::to_f2(kr.x), k23 = io<T>::to_f2(kr.y);
                 const float2 v01 = io<T>::to_f2(vr.x), v23 = io<T>::to_f2(vr.y);
 #pragma unroll
@@ -467,11 +479,8 @@ static int launch_dm4_t(const AttnArgs& a, const uint32_t* prepared, int gsub, c
     const size_t smem = dm4::kLutBytes + kVtabBytes + 32768 + 3072 + kWarps * kTile * 8 + (OUT ? 1024 : 256);
     static_assert(32768 + 3072 >= 2 * kWarps * 4 * 130 * sizeof(float) + 64, "stage area too small for the combine");
     static_assert(32768 + 3072 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
-    static bool configured = false;
-    if (!configured) {
-        MILLION_CUDA_OK(cudaFuncSetAttribute(attn_fast_dm4_kernel<T, G, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemAttrOnce configured = {};
+    MILLION_CUDA_OK(ensure_dynamic_smem(configured, attn_fast_dm4_kernel<T, G, OUT>, smem));
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
     if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
     attn_fast_dm4_kernel<T, G, OUT><<<grid, block, smem, stream>>>(a, prepared, gsub);

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
     const T* vcent = reinterpret_cast<const T*>(a.v_cent);
 
     int t0 = 0, t1 = 0;
-    if (window) t1 = a.r; else split_range(a, split, t0, t1);
+    if (window) t1 = window_rows(a); else split_range(a, split, t0, t1);
 
     for (int g = 0; g < G; ++g) {
         const int h = hk * G + g;

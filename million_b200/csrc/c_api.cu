@@ -66,15 +66,27 @@ static int encode_dispatch(const void* x, int x_dtype, int64_t xhs, const float*
         if (code_bytes != 1) MILLION_UNSUPPORTED("grid encoder writes one-byte codes");
         return launch_encode_grid(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, false);
     }
-    // AUTO: the tensor-core encoder pays off from a few hundred vectors on
+    // AUTO.  Two-dimensional sub-spaces: `prepared` holds the candidate-grid tables (million_pq_encoder_auto_prepare builds
+    // those for this shape) and the exact grid encoder runs — 4x the tensor-core encoder, bit-identical codes.
+    if (prepared != nullptr && code_bytes == 1 && encode_grid_prepared_bytes(d, M, C) > 0) {
+        if (launch_encode_grid(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, true) == MILLION_OK)
+            return launch_encode_grid(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, false);
+        return launch_encode_generic(x, x_dtype, xhs, cent, dst, n_heads, n_tokens, d, M, C, stream);   // the tables are not tensor-core tiles
+    }
+    // otherwise the tensor-core encoder, which pays off from a few hundred vectors on
     if ((int64_t)n_heads * n_tokens >= 256 &&
         launch_encode_tc(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, true) == MILLION_OK)
         return launch_encode_tc(x, x_dtype, xhs, cent, prepared, dst, n_heads, n_tokens, d, M, C, stream, false);
     return launch_encode_generic(x, x_dtype, xhs, cent, dst, n_heads, n_tokens, d, M, C, stream);
 }
 
+#ifdef MILLION_DEBUG
 static unsigned long long* g_dbg_timing = nullptr;
 static int g_dbg_mode = 0;
+#endif
+int launch_window_append_dev(void* k_win, void* v_win, int64_t win_hs_b, const void* k_new, const void* v_new, int n_heads, int row_bytes,
+                             const int* r_dev, int r_off, int res_len, cudaStream_t stream);
+int launch_counter_add(int* ctr, int n, int delta, cudaStream_t stream);
 static inline int elem_bytes(int dtype) { return dtype == MILLION_F32 ? 4 : 2; }
 
 }  // namespace million
@@ -105,6 +117,17 @@ int million_pq_encoder_prepare(const float* cent, int x_dtype, int d, int M, int
 }
 
 int64_t million_pq_encoder_grid_prepared_bytes(int d, int M, int C) { return encode_grid_prepared_bytes(d, M, C); }
+
+int64_t million_pq_encoder_auto_prepared_bytes(int d, int M, int C) {
+    const int64_t g = encode_grid_prepared_bytes(d, M, C);
+    return g > 0 ? g : encode_tc_prepared_bytes(d, M, C);
+}
+
+int million_pq_encoder_auto_prepare(const float* cent, int x_dtype, int d, int M, int C, void* prepared, million_stream_t stream) {
+    MILLION_REQUIRE(cent && prepared, "encoder_auto_prepare: null pointer");
+    if (encode_grid_prepared_bytes(d, M, C) > 0) return launch_encode_grid_prepare(cent, d, M, C, prepared, (cudaStream_t)stream);
+    return launch_encode_tc_prepare(cent, x_dtype, d, M, C, prepared, (cudaStream_t)stream);
+}
 
 int million_pq_encoder_grid_prepare(const float* cent, int d, int M, int C, void* prepared, million_stream_t stream) {
     MILLION_REQUIRE(cent && prepared, "encoder_grid_prepare: null pointer");
@@ -230,7 +253,10 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     MILLION_REQUIRE(p->q && p->k_cent && p->v_cent && p->workspace, "attn: null pointer");
     MILLION_REQUIRE(partial_only ? (p->partial != nullptr) : (p->out != nullptr), "attn: missing output pointer");
     MILLION_REQUIRE(p->nk == 0 || (p->k_codes && p->v_codes), "attn: null code pointer");
-    MILLION_REQUIRE(p->r == 0 || (p->k_res && p->v_res), "attn: null residual pointer");
+    MILLION_REQUIRE((p->r == 0 && p->r_dev == nullptr) || (p->k_res && p->v_res), "attn: null residual pointer");
+    MILLION_REQUIRE((p->k_new == nullptr) == (p->v_new == nullptr), "attn: k_new and v_new go together");
+    MILLION_REQUIRE(p->k_new == nullptr || p->r >= 1, "attn: with k_new/v_new, r counts the new token (r >= 1)");
+    MILLION_REQUIRE(p->k_new == nullptr || (p->d * 2) % 16 == 0, "attn: fused window append needs 16-byte rows");
     MILLION_REQUIRE(p->v_layout >= MILLION_V_ROWMAJOR && p->v_layout <= MILLION_V_PAGED, "attn: bad v_layout");
     if (p->v_layout == MILLION_V_PAGED && p->nk > 0) {
         MILLION_REQUIRE(p->v_page_ids && p->page_size > 0, "attn: paged V needs page ids and page_size");
@@ -272,20 +298,36 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
         MILLION_REQUIRE(p->v_out_head_stride >= (int64_t)p->nk * p->v_out, "attn: v_out_head_stride too small");
         a.v_out = p->v_out; a.vo_idx = p->v_out_idx; a.vo_val = p->v_out_val; a.vo_head_stride = p->v_out_head_stride;
     }
+    a.k_new = p->k_new; a.v_new = p->v_new; a.r_dev = p->r_dev;
+#ifdef MILLION_DEBUG
     a.dbg_timing = g_dbg_timing;
     a.dbg_mode = g_dbg_mode;
+#endif
 
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->impl == MILLION_IMPL_GENERIC) return launch_attn_generic(a, p->io_dtype, st);
-    if (p->impl == MILLION_IMPL_FAST) return launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, false);
-    if (launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, true) == MILLION_OK)
-        return launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, false);
+    const bool fast_ok = p->impl != MILLION_IMPL_GENERIC &&
+                         (p->impl == MILLION_IMPL_FAST || launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, true) == MILLION_OK);
+    if (fast_ok) return launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, false);   // appends the new token itself
+    if (a.k_new) {
+        // the all-shapes kernel reads the window only: append with a copy launch first (same device-resident row index)
+        int rc = launch_window_append_dev(const_cast<void*>(p->k_res), const_cast<void*>(p->v_res), (int64_t)p->res_len * p->d * 2, p->k_new, p->v_new,
+                                          p->bs * p->nh_k, p->d * 2, p->r_dev, p->r - 1, p->res_len, st);
+        if (rc != MILLION_OK) return rc;
+        a.k_new = a.v_new = nullptr;
+    }
     return launch_attn_generic(a, p->io_dtype, st);
 }
 
-/* debug hook (not part of the public header): per-CTA phase time stamps of the decode-attention kernels */
+#ifdef MILLION_DEBUG
+/* debug hooks (only in -DMILLION_DEBUG builds, not part of the public header): ablation switch and per-CTA phase time stamps */
 void million_debug_set_mode(int m) { g_dbg_mode = m; }
 void million_debug_set_timing_buffer(void* buf) { g_dbg_timing = reinterpret_cast<unsigned long long*>(buf); }
+#endif
+
+int million_counter_add(int32_t* ctr, int n, int delta, million_stream_t stream) {
+    MILLION_REQUIRE(ctr != nullptr && n >= 0, "counter_add: bad arguments");
+    return launch_counter_add(ctr, n, delta, (cudaStream_t)stream);
+}
 
 int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, million_stream_t stream) {
     MILLION_REQUIRE(parts && out && n_parts > 0 && n_rows >= 0 && d > 0, "lse_merge: bad arguments");

@@ -138,4 +138,42 @@ int launch_rows_copy2(void* k_dst, void* v_dst, int64_t dst_hs_b, int64_t dst_of
     return MILLION_OK;
 }
 
+// The new token's K and V rows -> window row (*r_dev + r_off), clamped to the window: the append of pq_utils.py:304-311 with the
+// row index read on the device (CUDA-graph replay of a decode step).  Used when the attention kernel does not append itself.
+__global__ void window_append_dev_kernel(unsigned char* k_win, unsigned char* v_win, int64_t win_hs_b, const unsigned char* k_new,
+                                         const unsigned char* v_new, int row_bytes, const int* r_dev, int r_off, int res_len) {
+    int row = (r_dev ? __ldg(r_dev) : 0) + r_off;
+    row = row < 0 ? 0 : (row >= res_len ? res_len - 1 : row);
+    const int head = blockIdx.x;
+    const bool isv = blockIdx.y;
+    unsigned char* dst = (isv ? v_win : k_win) + head * win_hs_b + (int64_t)row * row_bytes;
+    const unsigned char* src = (isv ? v_new : k_new) + (int64_t)head * row_bytes;
+    for (int i = threadIdx.x * 16; i < row_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+}
+
+int launch_window_append_dev(void* k_win, void* v_win, int64_t win_hs_b, const void* k_new, const void* v_new, int n_heads, int row_bytes,
+                             const int* r_dev, int r_off, int res_len, cudaStream_t stream) {
+    if (n_heads == 0) return MILLION_OK;
+    if (row_bytes % 16 || win_hs_b % 16 || ((uintptr_t)k_win | (uintptr_t)v_win | (uintptr_t)k_new | (uintptr_t)v_new) % 16) {
+        set_error("window append needs 16-byte aligned rows");
+        return MILLION_ERR_INVALID;
+    }
+    window_append_dev_kernel<<<dim3(n_heads, 2), 32, 0, stream>>>((unsigned char*)k_win, (unsigned char*)v_win, win_hs_b, (const unsigned char*)k_new,
+                                                                 (const unsigned char*)v_new, row_bytes, r_dev, r_off, res_len);
+    MILLION_CUDA_OK(cudaGetLastError());
+    return MILLION_OK;
+}
+
+__global__ void counter_add_kernel(int* ctr, int n, int delta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ctr[i] += delta;
+}
+
+int launch_counter_add(int* ctr, int n, int delta, cudaStream_t stream) {
+    if (n == 0) return MILLION_OK;
+    counter_add_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ctr, n, delta);
+    MILLION_CUDA_OK(cudaGetLastError());
+    return MILLION_OK;
+}
+
 }  // namespace million

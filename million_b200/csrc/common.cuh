@@ -42,6 +42,22 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: one flag per device, so a process that touches a
+// second GPU (device_map='auto', tests iterating over devices) configures the kernel there too.  Racing threads at worst set
+// the attribute twice.
+struct SmemAttrOnce { unsigned char done[64]; };
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(SmemAttrOnce& st, F func, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && st.done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && tracked) st.done[dev] = 1;
+    return e;
+}
+
 // ---------------------------------------------------------------- dtype traits
 template <typename T> struct io;
 template <> struct io<__half> {

@@ -410,11 +410,8 @@ int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C
 template <typename T, int DM>
 static int launch_tc_t(const tc::EncArgs& a, cudaStream_t stream) {
     const size_t smem = tc::kMG * tc::kBTileBytes + 4 * tc::kATileBytes + tc::kZeroBytes + 32 + 16 + tc::kMG * 4 + 64;
-    static bool configured = false;
-    if (!configured) {
-        MILLION_CUDA_OK(cudaFuncSetAttribute(tc::encode_tc_kernel<T, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemAttrOnce configured = {};
+    MILLION_CUDA_OK(ensure_dynamic_smem(configured, tc::encode_tc_kernel<T, DM>, smem));
     const int ygroups = a.M / tc::kMG;
     int sms = sm_count();
     if (sms <= 0) sms = 148;

@@ -90,19 +90,29 @@ def prepare_encoder_grid(cent_f32):
     return hit[0]
 
 
+def prepare_encoder_auto(cent_f32, x_dtype):
+    """The tables MILLION_IMPL_AUTO expects for this codebook shape (million_pq_encoder_auto_prepare): the candidate grid for
+    two-dimensional sub-spaces, the tensor-core tiles otherwise; None = no fast encoder for the shape (AUTO then runs the exact
+    CUDA-core encoder).  Same caches as the two specific functions."""
+    M, C, dm = cent_f32.shape
+    if L.lib().million_pq_encoder_grid_prepared_bytes(M * dm, M, C) > 0:
+        return prepare_encoder_grid(cent_f32)
+    return prepare_encoder(cent_f32, x_dtype)
+
+
 def _encoder_choice(X, cent_f32, impl, code_bytes):
-    """(impl, prepared) for one encode call: AUTO takes the candidate-grid encoder where it applies (two-dimensional
-    sub-spaces), else the tensor-core encoder, else the generic one (decided inside the library)."""
-    if code_bytes == 1 and impl in (L.IMPL_AUTO, L.IMPL_GRID):
+    """(impl, prepared) for one encode call.  AUTO is decided INSIDE the library (c_api.cu: grid encoder for d/M = 2, tensor-core
+    encoder for d/M = 4, exact CUDA-core encoder otherwise / for unaligned inputs); this only supplies the matching tables."""
+    if code_bytes != 1 or impl == L.IMPL_GENERIC:
+        return impl, None
+    if impl == L.IMPL_GRID:
         grid = prepare_encoder_grid(cent_f32)
-        if grid is not None:
-            eb = X.element_size()
-            if X.data_ptr() % (4 * eb) == 0:
-                return L.IMPL_GRID, grid
-        if impl == L.IMPL_GRID:
+        if grid is None or X.data_ptr() % (4 * X.element_size()):
             raise L.MillionError(L.MILLION_ERR_UNSUPPORTED, "grid encoder: shape or alignment not covered")
-    prep = prepare_encoder(cent_f32, X.dtype) if impl != L.IMPL_GENERIC and code_bytes == 1 else None
-    return impl, prep
+        return impl, grid
+    if impl == L.IMPL_FAST:
+        return impl, prepare_encoder(cent_f32, X.dtype)
+    return impl, prepare_encoder_auto(cent_f32, X.dtype)
 
 
 def pq_encode_into(X, cent_f32, codes, *, t0=0, layout="rowmajor", impl=L.IMPL_AUTO):
@@ -263,7 +273,7 @@ def prepare_codebooks(k_cent, v_cent):
 
 def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=None, v_layout=L.V_ROWMAJOR,
                    v_page_ids=None, page_size=0, out=None, partial=None, n_splits=0, impl=L.IMPL_AUTO, workspace=None,
-                   prepared=None, k_outliers=None, v_outliers=None, p2p=None):
+                   prepared=None, k_outliers=None, v_outliers=None, p2p=None, k_new=None, v_new=None, r_dev=None):
     """One decode-attention call (include/million_b200.h: million_pq_decode_attn).
 
     q (bs, nh, 1, d) | (bs, nh, d); k_codes (bs, nh_k, >=nk, M) uint8 (head stride taken from the tensor);
@@ -271,6 +281,9 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
     k_res/v_res (bs, nh_k, Lt, d).  Returns (bs, nh, 1, d) in q's dtype, or fills `partial` (bs, nh, d+2) fp32.
     k_outliers / v_outliers: optional (idx, val) side stores (bs, nh_k, >=nk, k_out) uint8 / q's dtype (extension).
     p2p = state tensor prepared by splitkv_state(): split-KV across GPUs fused into this launch (sharding.SplitKVPeerGroup).
+    k_new / v_new (bs, nh_k, 1, d) | (bs, nh_k, d): the token being decoded; the kernel stores it into window row r-1 itself (r
+    counts it) — the append of pq_utils.py:304-311 without a copy launch.  r_dev: int32 device scalar, the kernel then uses
+    r = *r_dev + r (CUDA-graph replay; see include/million_b200.h).
     """
     _need_cuda(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res)
     bs, nh = q.shape[0], q.shape[1]
@@ -327,14 +340,24 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
         if prepared is not None:
             p.prepared_codebook = prepared.data_ptr()
     p.res_len = k_res.shape[2] if k_res is not None else 0
-    if r:
+    if k_new is not None:
+        _need_cuda(k_new, v_new)
+        assert k_new.is_contiguous() and v_new.is_contiguous() and k_new.dtype == q.dtype and v_new.dtype == q.dtype
+        assert k_new.numel() == bs * nh_k * d and v_new.numel() == bs * nh_k * d and r >= 1
+        p.k_new, p.v_new = k_new.data_ptr(), v_new.data_ptr()
+    if r_dev is not None:
+        _need_cuda(r_dev)
+        assert r_dev.dtype == torch.int32
+        p.r_dev = r_dev.data_ptr()
+    if r or r_dev is not None:
         assert k_res.dtype == q.dtype and v_res.dtype == q.dtype
         # rows must be contiguous; a [:, :, :r] slice of a larger window is taken in place (res_len from the stride)
         def rows_ok(t):
             return t.stride(3) == 1 and t.stride(2) == d and t.stride(1) % d == 0 and (bs == 1 or t.stride(0) == nh_k * t.stride(1))
         if not (rows_ok(k_res) and rows_ok(v_res) and k_res.stride(1) == v_res.stride(1)):
+            assert k_new is None, "the kernel appends to the window in place: it needs contiguous rows"
             k_res, v_res = k_res.contiguous(), v_res.contiguous()
-        p.res_len = k_res.stride(1) // d if (nh_k > 1 or bs > 1) else max(k_res.shape[2], r)
+        p.res_len = k_res.stride(1) // d if (nh_k > 1 or bs > 1) else (k_res.shape[2] if (k_new is not None or r_dev is not None) else max(k_res.shape[2], r))
         p.k_res, p.v_res = k_res.data_ptr(), v_res.data_ptr()
     splits = n_splits or default_splits(bs, nh_k, nk)
     ws = workspace if workspace is not None else attn_workspace(q.device, bs, nh, nh_k, d, splits)
@@ -389,6 +412,13 @@ def window_append(k_win, v_win, k_new, v_new, r0):
     shs = k_new.stride(1) if nh > 1 else (k_new.stride(0) if bs > 1 else n * d)
     L.check(L.lib().million_window_append(_ptr(k_win), _ptr(v_win), Lt * d, _ptr(k_new), _ptr(v_new), shs, bs * nh, r0, n, d,
                                           _dt(k_win), _stream(k_win)))
+
+
+def counter_add(ctr, delta):
+    """ctr (int32, CUDA) += delta in one tiny launch of the library (graph capturable)."""
+    _need_cuda(ctr)
+    assert ctr.dtype == torch.int32 and ctr.is_contiguous()
+    L.check(L.lib().million_counter_add(_ptr(ctr), ctr.numel(), delta, _stream(ctr)))
 
 
 def window_shift(k_win, v_win, shift, rem):

@@ -248,8 +248,7 @@ class PagedPQCache(DynamicPQCache):
     def _encode_append(self, key_states, value_states, layer_idx, count_seen=True):
         """K codes row-major in place; V codes into pages through the block table.  Requires the V token count to
         be page aligned before the append (true for prefill-from-empty and for page-sized flushes)."""
-        if self._pending[layer_idx] is not None:
-            self._finish_async_flush(layer_idx)
+        self._complete_pending_flush(layer_idx)
         n = key_states.size(2)
         ks = self._k[layer_idx]
         self._reserve_k(layer_idx, n)
@@ -303,13 +302,14 @@ class PagedPQCache(DynamicPQCache):
     # ---- flush (paged_pq_utils.py:130-210)
     def flush_to_pages(self, layer_idx: int):
         """Quantize the oldest page_size window tokens into a fresh page per (b, h) and shift the window."""
-        if self._pending[layer_idx] is not None:
-            self._finish_async_flush(layer_idx)
-            self._after_flush_shift(layer_idx)
+        if self._complete_pending_flush(layer_idx):
             return
         if self.residualed_tokens[layer_idx] < self.page_size:
             return
         self._flush_window(layer_idx, self.page_size)
+        self._after_flush_shift(layer_idx)
+
+    def _window_after_flush(self, layer_idx):
         self._after_flush_shift(layer_idx)
 
     def _after_flush_shift(self, layer_idx):
@@ -341,23 +341,30 @@ class PagedPQCache(DynamicPQCache):
         self._pending[layer_idx] = None
 
     # ---- decode (paged_pq_utils.py:341-397)
-    def decoding_with_pages(self, query_states, key_states, value_states, layer_idx):
-        if self.residualed_tokens[layer_idx] >= self.extended_residual_size:
-            self.flush_to_pages(layer_idx)
+    def _window_full(self, layer_idx):
+        return self.residualed_tokens[layer_idx] >= self.extended_residual_size
+
+    def _flush_len(self):
+        return self.page_size
+
+    def _retire_window(self, layer_idx):
+        self.flush_to_pages(layer_idx)
+
+    def decoding_with_pages(self, query_states, key_states, value_states, layer_idx, out=None):
+        if self._window_full(layer_idx):
+            self._retire_window(layer_idx)
         r = self.residualed_tokens[layer_idx]
         n = key_states.size(2)
-        if (n == 1 and self.nbits == 8 and query_states.dtype == self.scalar_t and key_states.dtype == self.scalar_t
-                and query_states.is_contiguous() and key_states.is_contiguous() and value_states.is_contiguous()):
-            self._stats['paged_kernel_calls'] += 1
-            out = self._decode_fast(query_states, key_states, value_states, layer_idx, r)    # same two C calls, pre-filled params
-            if self.async_flush and self.residualed_tokens[layer_idx] >= self.extended_residual_size:
-                self._start_async_flush(layer_idx, self.page_size)
-            return out
-        ops.window_append(self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], key_states, value_states, r)
-        self.residualed_tokens[layer_idx] += n
-        self.seen_tokens[layer_idx] += n          # each token counted once (the reference double-counts, Appendix B.5)
-        out = self._call_paged_kernel(query_states, layer_idx, r + n)
-        if self.async_flush and self.residualed_tokens[layer_idx] >= self.extended_residual_size:
+        self._stats['paged_kernel_calls'] += 1
+        if self._fused_ok(query_states, key_states, value_states):
+            out = self._decode_fast(query_states, key_states, value_states, layer_idx, r, out)    # one C call, pre-filled params
+        else:
+            ops.window_append(self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], key_states, value_states, r)
+            self.residualed_tokens[layer_idx] += n
+            self.seen_tokens[layer_idx] += n          # each token counted once (the reference double-counts, Appendix B.5)
+            res = self._call_paged_kernel(query_states, layer_idx, r + n)
+            out = res if out is None else out.copy_(res)
+        if self.async_flush and self._window_full(layer_idx):
             self._start_async_flush(layer_idx, self.page_size)
         return out
 
@@ -375,7 +382,6 @@ class PagedPQCache(DynamicPQCache):
             # the reference's 13-argument paged call (paged_pq_utils.py:621-635) has no place for the side store
             ks = self._k[layer_idx]
             kc, vc = self._attn_cents(query_states.dtype)
-            self._stats['paged_kernel_calls'] += 1
             return ops.pq_decode_attn(query_states, ks.view(), self.page_managers[layer_idx].page_pool, kc, vc,
                                       self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], residual_length,
                                       v_layout=L.V_PAGED, v_page_ids=self._table[layer_idx], page_size=self.page_size,
@@ -387,7 +393,6 @@ class PagedPQCache(DynamicPQCache):
         kernel = getattr(bindings, name)
         kc, vc = self._attn_cents(query_states.dtype)
         n_pages = self._n_pages[layer_idx]
-        self._stats['paged_kernel_calls'] += 1
         ks = self._k[layer_idx]
         # pages may hold a partial tail: the kernel is told nk through key_codes, the table through n_pages
         return kernel(query_states, ks.view(), kc, self.key_residual_cache[layer_idx],
@@ -428,7 +433,4 @@ class PagedPQCache(DynamicPQCache):
 
     def cleanup(self):
         """paged_pq_utils.py:1082-1114."""
-        for l in range(self.layer_num):
-            if self._pending[l] is not None:
-                self._finish_async_flush(l)
-        self.init_cache()
+        self.init_cache()     # waits for in-flight flushes and drops every cached pointer (DynamicPQCache.init_cache)

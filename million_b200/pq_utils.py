@@ -241,6 +241,13 @@ class DynamicPQCache(metaclass=Singleton):
         """pq_utils.py:116-138."""
         if not self.device.type == 'cuda':
             raise RuntimeError("DynamicPQCache needs a CUDA device (no CPU path)")
+        # A reset (main_pq.py:363 uses init_cache as cache_clear_func) must not free memory an in-flight flush still writes,
+        # and must drop every cached raw pointer into the old windows / stores.
+        for pend in getattr(self, '_pending', ()):
+            if pend is not None:
+                pend[0].synchronize()
+        self._plans = {}
+        self._step_graph = None
         self._k = [self._new_store() for _ in range(self.layer_num)]
         self._v = [self._new_store() for _ in range(self.layer_num)]
         mk = lambda ko: [_OutlierStore(self.bs, self.num_key_value_heads, ko, self.scalar_t, self.device) if ko else None
@@ -274,6 +281,10 @@ class DynamicPQCache(metaclass=Singleton):
             self.value_cent = value_cent.contiguous()
         self._key_cent_f32 = self.key_cent.to(device=self.device, dtype=torch.float32).contiguous()
         self._value_cent_f32 = self.value_cent.to(device=self.device, dtype=torch.float32).contiguous()
+        # new codebooks: the attention-side casts, their gather tables and the per-layer launch plans are stale
+        self._attn_dtype = None
+        self._plans = {}
+        self._step_graph = None
         # encoder tables are built here, on the caller's stream, not lazily inside the first flush (which may run on the side
         # stream): every later use is ordered after this point
         for c in {id(self._key_cent_f32): self._key_cent_f32, id(self._value_cent_f32): self._value_cent_f32}.values():
@@ -322,8 +333,7 @@ class DynamicPQCache(metaclass=Singleton):
         return x
 
     def _encode_append(self, key_states, value_states, layer_idx, count_seen=True):
-        if self._pending[layer_idx] is not None:
-            self._finish_async_flush(layer_idx)
+        self._complete_pending_flush(layer_idx)
         n = key_states.size(2)
         ks, vs = self._k[layer_idx], self._v[layer_idx]
         self._reserve(layer_idx, n)
@@ -336,8 +346,7 @@ class DynamicPQCache(metaclass=Singleton):
 
     def cat_codes(self, key_codes, value_codes, layer_idx):
         """pq_utils.py:140-147 — kept for API compatibility: appends ready-made codes in place."""
-        if self._pending[layer_idx] is not None:
-            self._finish_async_flush(layer_idx)
+        self._complete_pending_flush(layer_idx)
         n = key_codes.size(2)
         ks, vs = self._k[layer_idx], self._v[layer_idx]
         ks.reserve(ks.len + n)
@@ -425,68 +434,91 @@ class DynamicPQCache(metaclass=Singleton):
         self._v[layer_idx].len += n
         self._pending[layer_idx] = None
 
-    # ---- decode
-    def decoding(self, query_states, key_states, value_states, layer_idx):
-        """pq_utils.py:281-327: flush a full window, append the new token to the window, run the kernel."""
-        if self.residualed_tokens[layer_idx] == self.max_residual_length:
-            if self._pending[layer_idx] is not None:
-                self._finish_async_flush(layer_idx)
-            else:
-                self._flush_window(layer_idx, self.max_residual_length)
-            self.residualed_tokens[layer_idx] = 0
+    def _window_after_flush(self, layer_idx):
+        """Window bookkeeping that belongs to a completed flush: the whole window was retired (pq_utils.py:299-301)."""
+        self.residualed_tokens[layer_idx] = 0
 
+    def _complete_pending_flush(self, layer_idx):
+        """The ONE place an in-flight flush is consumed: its codes become visible and the window forgets the flushed rows,
+        whoever asks first (the next decode step, a prefill/update/cat_codes that follows, a reset).  Returns True if there was one."""
+        if self._pending[layer_idx] is None:
+            return False
+        self._finish_async_flush(layer_idx)
+        self._window_after_flush(layer_idx)
+        return True
+
+    # ---- decode
+    def _window_full(self, layer_idx):
+        return self.residualed_tokens[layer_idx] == self.max_residual_length
+
+    def _flush_len(self):
+        return self.max_residual_length
+
+    def _retire_window(self, layer_idx):
+        """pq_utils.py:288-301: the full window becomes codes (already in flight when async_flush started it)."""
+        if not self._complete_pending_flush(layer_idx):
+            self._flush_window(layer_idx, self._flush_len())
+            self._window_after_flush(layer_idx)
+
+    def _fused_ok(self, q, k, v):
+        """One C call per layer (append fused into the attention launch): single token, cache dtype, plain aligned tensors."""
+        return (k.size(2) == 1 and self.nbits == 8 and q.dtype == self.scalar_t and k.dtype == self.scalar_t and v.dtype == self.scalar_t
+                and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+                and (k.data_ptr() | v.data_ptr()) % 16 == 0 and type(self)._fast_decode_ok)
+
+    def decoding(self, query_states, key_states, value_states, layer_idx, out=None):
+        """pq_utils.py:281-327: flush a full window, append the new token to the window, run the kernel.
+        `out` (extension): a preallocated (bs, nh, 1, d) result buffer."""
+        if self._window_full(layer_idx):
+            self._retire_window(layer_idx)
         r = self.residualed_tokens[layer_idx]
         n = key_states.size(2)
-        if (n == 1 and self.nbits == 8 and query_states.dtype == self.scalar_t and key_states.dtype == self.scalar_t
-                and query_states.is_contiguous() and key_states.is_contiguous() and value_states.is_contiguous()
-                and type(self)._fast_decode_ok):
-            out = self._decode_fast(query_states, key_states, value_states, layer_idx, r)
-            if self.async_flush and self.residualed_tokens[layer_idx] == self.max_residual_length:
-                self._start_async_flush(layer_idx, self.max_residual_length)
-            return out
-        ops.window_append(self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], key_states, value_states, r)
-        self.residualed_tokens[layer_idx] += n
-        self.seen_tokens[layer_idx] += n
-
-        kc, vc = self._attn_cents(query_states.dtype)
-        if self.k_out or self.v_out:
-            # the reference's 10-argument kernel signature (pq_utils.py:83-94) has no place for the side store
-            ks = self._k[layer_idx]
-            out = ops.pq_decode_attn(query_states, ks.view(), self._v[layer_idx].view(), kc, vc,
-                                     self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
-                                     self.residualed_tokens[layer_idx],
-                                     k_outliers=self._ko[layer_idx].view(ks.len) if self.k_out else None,
-                                     v_outliers=self._vo[layer_idx].view(ks.len) if self.v_out else None)
-            if self.async_flush and self.residualed_tokens[layer_idx] == self.max_residual_length:
-                self._start_async_flush(layer_idx, self.max_residual_length)
-            return out
-        kernel = self.registery.get_kernel(l=self.seen_tokens[layer_idx])
-        out = kernel(query_states, self._k[layer_idx].view(), self._v[layer_idx].view(), kc, vc,
-                     self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
-                     self.residualed_tokens[layer_idx])
-        if self.async_flush and self.residualed_tokens[layer_idx] == self.max_residual_length:
-            self._start_async_flush(layer_idx, self.max_residual_length)
+        if self._fused_ok(query_states, key_states, value_states):
+            out = self._decode_fast(query_states, key_states, value_states, layer_idx, r, out)
+        else:
+            ops.window_append(self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx], key_states, value_states, r)
+            self.residualed_tokens[layer_idx] += n
+            self.seen_tokens[layer_idx] += n
+            res = self._decode_registry(query_states, layer_idx)
+            out = res if out is None else out.copy_(res)
+        if self.async_flush and self._window_full(layer_idx):
+            self._start_async_flush(layer_idx, self._flush_len())
         return out
 
-    # ---- the same two C-ABI calls (window append + attention) without the Python layers in between
+    def _decode_registry(self, query_states, layer_idx):
+        """The reference's route: KernelRegistry -> named binding (pq_utils.py:313-327); side stores go through ops directly."""
+        kc, vc = self._attn_cents(query_states.dtype)
+        ks = self._k[layer_idx]
+        if self.k_out or self.v_out:
+            # the reference's 10-argument kernel signature (pq_utils.py:83-94) has no place for the side store
+            return ops.pq_decode_attn(query_states, ks.view(), self._v[layer_idx].view(), kc, vc,
+                                      self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
+                                      self.residualed_tokens[layer_idx],
+                                      k_outliers=self._ko[layer_idx].view(ks.len) if self.k_out else None,
+                                      v_outliers=self._vo[layer_idx].view(ks.len) if self.v_out else None)
+        kernel = self.registery.get_kernel(l=self.seen_tokens[layer_idx])
+        return kernel(query_states, ks.view(), self._v[layer_idx].view(), kc, vc,
+                      self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
+                      self.residualed_tokens[layer_idx])
+
+    # ---- the same step as ONE C-ABI call per layer (window append fused into the attention launch), without the Python layers
     _fast_decode_ok = True
 
     def _fill_v(self, p, layer_idx):
         vs = self._v[layer_idx]
         p.v_layout, p.v_codes, p.v_head_stride = L.V_ROWMAJOR, vs.buf.data_ptr(), vs.cap * self.M
 
-    def _decode_fast(self, q, k, v, layer_idx, r):
-        """One decode step of one layer: exactly what decoding() does through KernelRegistry -> bindings -> ops, but with a
-        per-layer, pre-filled million_attn_params (the per-call Python work is what bounds batch-1 decode)."""
+    def _plan(self, layer_idx, dtype, device):
+        """Per-layer, pre-filled million_attn_params (the per-call Python work is what bounds batch-1 decode).  Dropped by
+        init_cache() and set_cent(): it holds raw pointers into the windows and the codebook tables."""
         import ctypes
-        plans = self.__dict__.setdefault('_plans', {})
-        plan = plans.get(layer_idx)
-        kc, vc = self._attn_cents(q.dtype)
+        plan = self._plans.get(layer_idx)
+        kc, vc = self._attn_cents(dtype)
         if plan is None or plan['cent'] is not kc:
             lib = L.lib()
             p = L.AttnParams()
             p.struct_size = ctypes.sizeof(L.AttnParams)
-            p.io_dtype = ops._DT[q.dtype]
+            p.io_dtype = ops._DT[dtype]
             p.impl, p.flags = L.IMPL_AUTO, 0
             p.bs, p.nh, p.nh_k, p.d, p.M, p.C = self.bs, self.nh, self.num_key_value_heads, self.d, self.M, kc.shape[1]
             p.v_layout = L.V_ROWMAJOR
@@ -497,23 +529,16 @@ class DynamicPQCache(metaclass=Singleton):
             if prepared is not None:
                 p.prepared_codebook = prepared.data_ptr()
             max_splits = ops.default_splits(self.bs, self.num_key_value_heads, 1 << 30)
-            ws = ops.attn_workspace(q.device, self.bs, self.nh, self.num_key_value_heads, self.d, max_splits)
+            ws = ops.attn_workspace(device, self.bs, self.nh, self.num_key_value_heads, self.d, max_splits)
             p.workspace, p.workspace_bytes, p.n_splits = ws.data_ptr(), ws.numel(), 0
-            plan = dict(p=p, ref=ctypes.byref(p), cent=kc, keep=(prepared, ws, vc), attn=lib.million_pq_decode_attn,
-                        append=lib.million_window_append, heads=self.bs * self.num_key_value_heads,
-                        win=(ctypes.c_void_p(p.k_res), ctypes.c_void_p(p.v_res)), dt=ops._DT[q.dtype])
-            plans[layer_idx] = plan
-        p = plan['p']
-        stream = ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
-        st = plan['append'](plan['win'][0], plan['win'][1], self.max_residual_length * self.d, ctypes.c_void_p(k.data_ptr()),
-                            ctypes.c_void_p(v.data_ptr()), self.d, plan['heads'], r, 1, self.d, plan['dt'], stream)
-        if st:
-            L.check(st)
-        self.residualed_tokens[layer_idx] = r + 1
-        self.seen_tokens[layer_idx] += 1
+            plan = dict(p=p, ref=ctypes.byref(p), cent=kc, keep=(prepared, ws, vc), attn=lib.million_pq_decode_attn)
+            self._plans[layer_idx] = plan
+        return plan
+
+    def _fill_stores(self, p, layer_idx):
+        """Current code stores (and side stores) of a layer -> the launch parameters."""
         ks = self._k[layer_idx]
-        out = torch.empty(self.bs, self.nh, 1, self.d, dtype=q.dtype, device=q.device)
-        p.q, p.out, p.nk, p.r = q.data_ptr(), out.data_ptr(), ks.len, r + 1
+        p.nk = ks.len
         if ks.len:
             p.k_codes, p.k_head_stride = ks.buf.data_ptr(), ks.cap * self.M
             self._fill_v(p, layer_idx)
@@ -523,10 +548,29 @@ class DynamicPQCache(metaclass=Singleton):
             if self.v_out:
                 vo = self._vo[layer_idx]
                 p.v_out, p.v_out_idx, p.v_out_val, p.v_out_head_stride = self.v_out, vo.idx.data_ptr(), vo.val.data_ptr(), vo.cap * self.v_out
-        st = plan['attn'](plan['ref'], stream)
+
+    def _decode_fast(self, q, k, v, layer_idx, r, out=None):
+        """One decode step of one layer: what decoding() does through window_append + KernelRegistry -> bindings -> ops, as one
+        launch (k_new / v_new of million_attn_params: the kernel stores the new token into window row r itself)."""
+        import ctypes
+        plan = self._plan(layer_idx, q.dtype, q.device)
+        p = plan['p']
+        if out is None:
+            out = torch.empty(self.bs, self.nh, 1, self.d, dtype=q.dtype, device=q.device)
+        p.q, p.out, p.k_new, p.v_new, p.r, p.r_dev = q.data_ptr(), out.data_ptr(), k.data_ptr(), v.data_ptr(), r + 1, None
+        self._fill_stores(p, layer_idx)
+        st = plan['attn'](plan['ref'], ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream))
         if st:
             L.check(st)
+        self.residualed_tokens[layer_idx] = r + 1
+        self.seen_tokens[layer_idx] += 1
         return out
+
+    def decode_step_graph(self, q, k, v, out):
+        """CUDA-graph replay of one decode step of ALL layers over static buffers (extension; the reference calls decoding()
+        layer by layer from Python, modeling_llama.py:529-547): q/out (layers, bs, nh, 1, d), k/v (layers, bs, nh_k, 1, d).
+        Returns a DecodeStepGraph; call .step() once per token after filling q, k, v."""
+        return DecodeStepGraph(self, q, k, v, out)
 
     # ---- size properties (pq_utils.py:383-408)
     @property
@@ -554,3 +598,90 @@ class DynamicPQCache(metaclass=Singleton):
     def registry_size(self):
         return (sum(b.numel() * b.element_size() for b in self.registery.partial_out_buffers.values())
                 + sum(b.numel() * b.element_size() for b in self.registery.partial_lse_buffers.values()))
+
+
+class DecodeStepGraph:
+    """One decode step of every layer of a DynamicPQCache / PagedPQCache as a CUDA graph.
+
+    The captured launches carry no per-token host value: the window length lives in a device counter (million_attn_params.r_dev,
+    bumped by million_counter_add at the end of the graph), each layer is ONE launch (window append fused), inputs and outputs
+    are the caller's static buffers.  The cache POLICY stays on the host and is the one of decoding() (pq_utils.py:281-327,
+    paged_pq_utils.py:341-397): before a step, full windows are retired into codes; the graph is re-captured when the code
+    stores changed (every Lt = 128 tokens, 64 for the paged cache) — their lengths and addresses are launch parameters."""
+
+    def __init__(self, cache, q, k, v, out):
+        c = cache
+        Ln = c.layer_num
+        assert q.shape == (Ln, c.bs, c.nh, 1, c.d) and out.shape == q.shape and k.shape == (Ln, c.bs, c.num_key_value_heads, 1, c.d) and v.shape == k.shape
+        for t in (q, k, v, out):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == c.scalar_t
+        assert c._fused_ok(q[0], k[0], v[0]), "decode_step_graph needs nbits=8 and fp16/bf16 buffers in the cache dtype"
+        self.cache, self.q, self.k, self.v, self.out = c, q, k, v, out
+        self.r_dev = torch.zeros(1, dtype=torch.int32, device=q.device)
+        self._r_host = 0
+        self.graph, self.sig, self.captures = None, None, 0
+
+    def _launch_all(self):
+        import ctypes
+        c = self.cache
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.q.device).cuda_stream)
+        sig = []
+        for l in range(c.layer_num):
+            plan = c._plan(l, self.q.dtype, self.q.device)
+            p = plan['p']
+            p.q, p.out, p.k_new, p.v_new = self.q[l].data_ptr(), self.out[l].data_ptr(), self.k[l].data_ptr(), self.v[l].data_ptr()
+            p.r, p.r_dev = 1, self.r_dev.data_ptr()
+            c._fill_stores(p, l)
+            st = plan['attn'](plan['ref'], stream)
+            if st:
+                L.check(st)
+            p.r_dev = None
+            sig.append((p.nk, p.k_codes, p.k_head_stride, p.v_codes, p.v_head_stride, p.v_page_ids, p.n_pages, p.k_out_idx, p.v_out_idx, p.k_res))
+        ops.counter_add(self.r_dev, 1)
+        return sig
+
+    def _signature(self):
+        c = self.cache
+        sig = []
+        for l in range(c.layer_num):
+            p = c._plan(l, self.q.dtype, self.q.device)['p']
+            c._fill_stores(p, l)
+            sig.append((p.nk, p.k_codes, p.k_head_stride, p.v_codes, p.v_head_stride, p.v_page_ids, p.n_pages, p.k_out_idx, p.v_out_idx, p.k_res))
+        return sig
+
+    def _capture(self, r):
+        # warm-up on the current stream (first-use attributes), then capture; both write window row r from the static buffers,
+        # which the replay writes again with the same values
+        self.r_dev.fill_(r)
+        self._launch_all()
+        self.r_dev.fill_(r)
+        torch.cuda.current_stream(self.q.device).synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.sig = self._launch_all()
+        self.graph = g
+        self.captures += 1
+        self._r_host = r
+
+    def step(self):
+        c = self.cache
+        for l in range(c.layer_num):
+            if c._window_full(l):
+                c._retire_window(l)
+        r = c.residualed_tokens[0]
+        assert all(x == r for x in c.residualed_tokens), "decode_step_graph steps all layers together"
+        if self.graph is None or c._step_graph is not self or self._signature() != self.sig:
+            c._step_graph = self
+            self._capture(r)
+        elif self._r_host != r:
+            self.r_dev.fill_(r)
+            self._r_host = r
+        self.graph.replay()
+        self._r_host = r + 1
+        for l in range(c.layer_num):
+            c.residualed_tokens[l] = r + 1
+            c.seen_tokens[l] += 1
+        if c.async_flush and c._window_full(0):
+            for l in range(c.layer_num):
+                c._start_async_flush(l, c._flush_len())
+        return self.out

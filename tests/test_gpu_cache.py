@@ -143,12 +143,14 @@ def test_dynamic_cache_batched_gqa_bf16(dtype, bs, nh, nh_k, M):
     cache.set_cent(kc.cuda(), vc.cuda())
     oracle = O.DynamicPQCacheOracle(**kw)
     oracle.set_cent(kc.float().numpy(), vc.float().numpy())
-    atol = ATOL if dtype == torch.float16 else 8e-3
+    atol = ATOL
     for layer in (0, 1):
         q, k, v = mk(bs, nh, 70, 128), mk(bs, nh_k, 70, 128), mk(bs, nh_k, 70, 128)
         out = cache.prefill(q.cuda(), k.cuda(), v.cuda(), layer)
         ref = oracle.prefill(q.float().numpy(), k.float().numpy(), v.float().numpy(), layer)
-        np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=2 * atol, rtol=RTOL)
+        # prefill attention is torch's SDPA in the model dtype — library code, the same call the reference makes
+        # (pq_utils.py:253-260): in bf16 it rounds P to 8 bits before PV, so ITS tolerance applies here, not the PQ kernel's
+        np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=atol if dtype == torch.float16 else 1.6e-2, rtol=RTOL)
     for step in range(135):
         for layer in (0, 1):
             q, k, v = mk(bs, nh, 1, 128), mk(bs, nh_k, 1, 128), mk(bs, nh_k, 1, 128)

@@ -1,0 +1,417 @@
+"""GPU: round-2 parity cases — the sizes the bench times (against the pinned C oracle, with a scaled-error assertion next to
+the absolute one), the fused window append / device-resident window length / CUDA-graph decode step, the cache reset and
+codebook replacement paths, paged prefill at 32K (block table + pool bit-exact), Llama-2-7B (MHA) shapes with the outlier
+store, and the C ABI's own encoder choice."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as CO
+from oracle import pq_oracle as O
+
+pytestmark = pytest.mark.gpu
+ATOL, RTOL = 2e-3, 1e-2      # north_star: max-abs 2e-3 / relative 1e-2
+REL_TO_SIGNAL = 2e-2         # max |err| <= 2 % of max |ref|: on randn data at 32K+ the outputs are ~1e-2, so ATOL alone says little
+
+
+@pytest.fixture(scope="module")
+def M():
+    from million_b200 import ops
+    return ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _mk(cls, **kw):
+    from million_b200.pq_utils import Singleton
+    Singleton.clear_instance()
+    return cls(**kw)
+
+
+def _c_oracle(inp, r):
+    f = lambda k: np.ascontiguousarray(inp[k].astype(np.float32))
+    return CO.pq_decode_attn(f("q"), inp["kc"], inp["vc"], f("kcent"), f("vcent"), f("kres"), f("vres"), r)
+
+
+def _check(out, ref, what=""):
+    out = out.float().cpu().numpy().reshape(ref.shape)
+    err = np.abs(out - ref).max()
+    sig = np.abs(ref).max()
+    print(f"{what}: max|err| {err:.3e}, max|ref| {sig:.3e}, scaled {err / sig:.3e}")
+    np.testing.assert_allclose(out, ref, atol=ATOL, rtol=RTOL)
+    assert err <= REL_TO_SIGNAL * sig, f"{what}: error {err:.3e} is {err / sig:.1%} of the signal {sig:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ the launches bench.py times
+
+
+@pytest.mark.parametrize("bs,ctx", [(8, 32768), (1, 32768), (1, 131072)])
+def test_headline_shapes_against_c_oracle(M, bs, ctx):
+    """BASELINE configs 2 and 4 at FULL size (Llama-3.1-8B shapes, 4-bit PQ, window 128): exactly the launch bench.py times,
+    against the pinned C oracle (oracle/pq_oracle.c) on the same inputs."""
+    nk, r = ctx - 128, 128
+    inp = O.make_inputs(bs=bs, nh=32, nh_k=8, nk=nk, d=128, M=64, C=256, Lt=128, seed=42)
+    t = {k: dev(v) for k, v in inp.items()}
+    out = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r)
+    _check(out, _c_oracle(inp, r), f"bs{bs} ctx{ctx}")
+
+
+def test_headline_shape_self_consistent_codes(M):
+    """Same size, but the codes come from ENCODING randn K/V (attention over self-consistent data: scores are peaked around
+    the keys that resemble q), bf16 I/O at north_star's tolerance."""
+    bs, nk, r = 2, 32768 - 128, 128
+    inp = O.make_inputs(bs=bs, nh=32, nh_k=8, nk=nk, d=128, M=64, C=256, Lt=128, seed=7, self_consistent=True)
+    for dtype in (torch.float16, torch.bfloat16):
+        t = {k: dev(v) for k, v in inp.items()}
+        for k in ("q", "kcent", "vcent", "kres", "vres"):
+            t[k] = t[k].to(dtype)
+        rounded = dict(inp)
+        for k in ("q", "kcent", "vcent", "kres", "vres"):
+            rounded[k] = t[k].float().cpu().numpy()
+        out = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r)
+        _check(out, _c_oracle(rounded, r), f"self-consistent {dtype}")
+
+
+# ------------------------------------------------------------------------------------------------ fused window append, r_dev
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("nh,nh_k,Mm,v_layout", [(32, 8, 64, 0), (8, 8, 64, 0), (16, 8, 64, 1), (32, 8, 32, 0), (8, 4, 16, 0)])
+def test_fused_append_equals_append_then_attend(M, impl, nh, nh_k, Mm, v_layout):
+    """k_new / v_new of million_attn_params: the launch stores the new token into window row r-1 and attends over it.  Must be
+    bit-identical to million_window_append followed by the plain call, for every kernel (fast M=64, fast M=32, generic) — and
+    with the window length read from device memory (r_dev)."""
+    from million_b200 import _lib as L
+    bs, nk = 2, 1500
+    inp = O.make_inputs(bs=bs, nh=nh, nh_k=nh_k, nk=nk, d=128, M=Mm, C=256, Lt=128, seed=nh + Mm)
+    t = {k: dev(v) for k, v in inp.items()}
+    vc = t["vc"].transpose(2, 3).contiguous() if v_layout == 1 else t["vc"]
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    for r0 in (0, 16, 127):
+        k_new = torch.randn(bs, nh_k, 1, 128, device="cuda", generator=g).half()
+        v_new = torch.randn(bs, nh_k, 1, 128, device="cuda", generator=g).half()
+        kw1, vw1 = t["kres"].clone(), t["vres"].clone()
+        M.window_append(kw1, vw1, k_new, v_new, r0)
+        want = M.pq_decode_attn(t["q"], t["kc"], vc, t["kcent"], t["vcent"], kw1, vw1, r0 + 1, nk=nk, v_layout=v_layout, impl=impl)
+        kw2, vw2 = t["kres"].clone(), t["vres"].clone()
+        got = M.pq_decode_attn(t["q"], t["kc"], vc, t["kcent"], t["vcent"], kw2, vw2, r0 + 1, nk=nk, v_layout=v_layout, impl=impl,
+                               k_new=k_new, v_new=v_new)
+        assert torch.equal(got, want) and torch.equal(kw2, kw1) and torch.equal(vw2, vw1)
+        kw3, vw3 = t["kres"].clone(), t["vres"].clone()
+        r_dev = torch.tensor([r0], dtype=torch.int32, device="cuda")
+        got = M.pq_decode_attn(t["q"], t["kc"], vc, t["kcent"], t["vcent"], kw3, vw3, 1, nk=nk, v_layout=v_layout, impl=impl,
+                               k_new=k_new, v_new=v_new, r_dev=r_dev)
+        assert torch.equal(got, want) and torch.equal(kw3, kw1) and torch.equal(vw3, vw1)
+        M.counter_add(r_dev, 1)
+        assert int(r_dev.item()) == r0 + 1
+    ref = O.pq_decode_attn(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], kw1.float().cpu().numpy(), vw1.float().cpu().numpy(), 128)
+    np.testing.assert_allclose(want.float().cpu().numpy(), ref, atol=ATOL, rtol=RTOL)
+
+
+def _cents(seed, M_=64):
+    rng = np.random.default_rng(seed)
+    mk = lambda: rng.standard_normal((M_, 256, 128 // M_), dtype=np.float32).astype(np.float16)
+    return mk(), mk()
+
+
+@pytest.mark.parametrize("paged", [False, True])
+@pytest.mark.parametrize("async_flush", [False, True])
+def test_decode_step_graph_follows_the_oracle_policy(paged, async_flush):
+    """decode_step_graph(): every layer of a step in one CUDA graph, window length on the device.  Outputs, counters and codes
+    must follow the oracle's restatement of the reference policy across several flushes (the graph is re-captured there)."""
+    from million_b200.paged_pq_utils import PagedPQCache
+    from million_b200.pq_utils import DynamicPQCache
+    layers, bs, nh, nh_k, d = 3, 2, 8, 2, 128
+    kw = dict(bs=bs, nh=nh, num_key_value_heads=nh_k, M=64, layer_num=layers, d=d)
+    kc, vc = _cents(5)
+    cache = _mk(PagedPQCache if paged else DynamicPQCache, scalar_t=torch.float16, async_flush=async_flush, **kw)
+    cache.set_cent(dev(kc), dev(vc))
+    oracle = (O.PagedPQCacheOracle if paged else O.DynamicPQCacheOracle)(**kw)
+    oracle.set_cent(kc, vc)
+    rng = np.random.default_rng(3)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32).astype(np.float16)
+    T0 = 128 if paged else 41
+    for l in range(layers):
+        q, k, v = f(bs, nh, T0, d), f(bs, nh_k, T0, d), f(bs, nh_k, T0, d)
+        cache.prefill(dev(q), dev(k), dev(v), l)
+        oracle.prefill(q, k, v, l)
+    dq = torch.empty(layers, bs, nh, 1, d, dtype=torch.float16, device="cuda")
+    dk = torch.empty(layers, bs, nh_k, 1, d, dtype=torch.float16, device="cuda")
+    dv, do = torch.empty_like(dk), torch.empty_like(dq)
+    step = cache.decode_step_graph(dq, dk, dv, do)
+    name = "decoding_with_pages" if paged else "decoding"
+    for i in range(300):
+        q, k, v = f(layers, bs, nh, 1, d), f(layers, bs, nh_k, 1, d), f(layers, bs, nh_k, 1, d)
+        dq.copy_(dev(q)); dk.copy_(dev(k)); dv.copy_(dev(v))
+        out = step.step().float().cpu().numpy()
+        for l in range(layers):
+            ref = getattr(oracle, name)(q[l], k[l], v[l], l)
+            np.testing.assert_allclose(out[l], ref, atol=ATOL, rtol=RTOL, err_msg=f"step {i} layer {l}")
+        assert cache.residualed_tokens == oracle.residualed_tokens
+        if not paged:      # the paged reference double-counts flushed tokens; ours counts once
+            assert cache.seen_tokens == oracle.seen_tokens
+    torch.cuda.synchronize()
+    assert 3 <= step.captures <= 8          # one capture per flush epoch, not per token
+    for l in range(layers):
+        nkq = oracle.key_cache[l].shape[2]
+        assert np.array_equal(cache.key_cache[l].cpu().numpy()[:, :, :nkq], oracle.key_cache[l])
+
+
+def test_graph_step_and_eager_decoding_agree_bitwise():
+    from million_b200.pq_utils import DynamicPQCache
+    layers, bs, nh, nh_k, d = 2, 1, 32, 8, 128
+    kw = dict(bs=bs, nh=nh, num_key_value_heads=nh_k, M=64, layer_num=layers, d=d)
+    kc, vc = _cents(9)
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    pre = [torch.randn(3, bs, nh_k, 700, d, device="cuda", generator=g).half() for _ in range(layers)]
+    steps = [(torch.randn(layers, bs, nh, 1, d, device="cuda", generator=g).half(), torch.randn(layers, bs, nh_k, 1, d, device="cuda", generator=g).half(),
+              torch.randn(layers, bs, nh_k, 1, d, device="cuda", generator=g).half()) for _ in range(140)]
+    outs = []
+    for mode in ("eager", "graph"):
+        cache = _mk(DynamicPQCache, scalar_t=torch.float16, **kw)
+        cache.set_cent(dev(kc), dev(vc))
+        for l in range(layers):
+            cache.prefill(pre[l][0].repeat_interleave(nh // nh_k, 1), pre[l][1], pre[l][2], l)
+        res = []
+        if mode == "graph":
+            dq, dk, dv = torch.empty_like(steps[0][0]), torch.empty_like(steps[0][1]), torch.empty_like(steps[0][2])
+            do = torch.empty_like(dq)
+            gs = cache.decode_step_graph(dq, dk, dv, do)
+        for q, k, v in steps:
+            if mode == "eager":
+                res.append(torch.stack([cache.decoding(q[l], k[l], v[l], l) for l in range(layers)]))
+            else:
+                dq.copy_(q); dk.copy_(k); dv.copy_(v)
+                res.append(gs.step().clone())
+        outs.append(torch.stack(res))
+        torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------------------------------------ reset / new codebooks / pending flush
+
+
+@pytest.mark.parametrize("paged", [False, True])
+def test_init_cache_reset_equals_fresh_cache(paged):
+    """main_pq.py:363 uses init_cache() as the reset between samples: afterwards the cache must behave like a new one (no stale
+    window pointers in the launch plans, no flush still writing into freed stores)."""
+    from million_b200.paged_pq_utils import PagedPQCache
+    from million_b200.pq_utils import DynamicPQCache
+    cls = PagedPQCache if paged else DynamicPQCache
+    kw = dict(bs=1, nh=8, num_key_value_heads=2, M=64, layer_num=2, d=128)
+    kc, vc = _cents(11)
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    T0 = 128
+    pre = [torch.randn(1, 8, T0, 128, device="cuda", generator=g).half(), torch.randn(1, 2, T0, 128, device="cuda", generator=g).half(),
+           torch.randn(1, 2, T0, 128, device="cuda", generator=g).half()]
+    toks = [(torch.randn(1, 8, 1, 128, device="cuda", generator=g).half(), torch.randn(1, 2, 1, 128, device="cuda", generator=g).half(),
+             torch.randn(1, 2, 1, 128, device="cuda", generator=g).half()) for _ in range(200)]
+
+    def run(cache, n):
+        outs = []
+        for l in range(2):
+            cache.prefill(*pre, l)
+        for q, k, v in toks[:n]:
+            outs.append(torch.stack([cache.decoding(q, k, v, l).clone() for l in range(2)]))
+        return torch.stack(outs)
+
+    cache = _mk(cls, scalar_t=torch.float16, **kw)
+    cache.set_cent(dev(kc), dev(vc))
+    run(cache, 128)       # ends with a flush in flight (async_flush) and a populated plan cache
+    assert cache._pending[0] is not None and cache._plans
+    junk = [torch.full((1, 2, 128, 128), 7.0, device="cuda", dtype=torch.float16) for _ in range(8)]   # recycle freed window blocks
+    cache.init_cache() if not paged else cache.cleanup()
+    del junk
+    again = run(cache, 200)
+    fresh = _mk(cls, scalar_t=torch.float16, **kw)
+    fresh.set_cent(dev(kc), dev(vc))
+    want = run(fresh, 200)
+    torch.cuda.synchronize()
+    assert torch.equal(again, want)
+    assert cache.seen_tokens == fresh.seen_tokens and cache.residualed_tokens == fresh.residualed_tokens
+
+
+def test_set_cent_twice_switches_attention_codebooks():
+    from million_b200.pq_utils import DynamicPQCache
+    kw = dict(bs=1, nh=8, num_key_value_heads=2, M=64, layer_num=1, d=128)
+    g = torch.Generator(device="cuda"); g.manual_seed(6)
+    pre = [torch.randn(1, 8, 300, 128, device="cuda", generator=g).half(), torch.randn(1, 2, 300, 128, device="cuda", generator=g).half(),
+           torch.randn(1, 2, 300, 128, device="cuda", generator=g).half()]
+    tok = [torch.randn(1, 8, 1, 128, device="cuda", generator=g).half(), torch.randn(1, 2, 1, 128, device="cuda", generator=g).half(),
+           torch.randn(1, 2, 1, 128, device="cuda", generator=g).half()]
+    cache = _mk(DynamicPQCache, scalar_t=torch.float16, **kw)
+    kc1, vc1 = _cents(1)
+    kc2, vc2 = _cents(2)
+    cache.set_cent(dev(kc1), dev(vc1))
+    cache.prefill(*pre, 0)
+    cache.decoding(*tok, 0)
+    cache.init_cache()
+    cache.set_cent(dev(kc2), dev(vc2))          # the singleton is reused across runs with new centroids
+    cache.prefill(*pre, 0)
+    got = cache.decoding(*tok, 0)
+    oracle = O.DynamicPQCacheOracle(**kw)
+    oracle.set_cent(kc2, vc2)
+    h = lambda t: t.float().cpu().numpy()
+    oracle.prefill(*[h(x) for x in pre], 0)
+    ref = oracle.decoding(*[h(x) for x in tok], 0)
+    np.testing.assert_allclose(h(got), ref, atol=ATOL, rtol=RTOL)
+
+
+@pytest.mark.parametrize("paged", [False, True])
+def test_prefill_after_window_filled_consumes_the_pending_flush_once(paged):
+    """A prefill/update right after the decode step that filled the window (flush already in flight): the flushed rows must
+    leave the window exactly once — no token stored twice, none attended twice."""
+    from million_b200.paged_pq_utils import PagedPQCache
+    from million_b200.pq_utils import DynamicPQCache
+    cls = PagedPQCache if paged else DynamicPQCache
+    kw = dict(bs=1, nh=8, num_key_value_heads=2, M=64, layer_num=1, d=128)
+    kc, vc = _cents(13)
+    cache = _mk(cls, scalar_t=torch.float16, async_flush=True, **kw)
+    cache.set_cent(dev(kc), dev(vc))
+    rng = np.random.default_rng(8)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32).astype(np.float16)
+    allk, allv = [], []
+
+    def feed_prefill(n):
+        q, k, v = f(1, 8, n, 128), f(1, 2, n, 128), f(1, 2, n, 128)
+        cache.prefill(dev(q), dev(k), dev(v), 0)
+        allk.append(k); allv.append(v)
+
+    def feed_decode():
+        q, k, v = f(1, 8, 1, 128), f(1, 2, 1, 128), f(1, 2, 1, 128)
+        allk.append(k); allv.append(v)
+        return q, cache.decoding(dev(q), dev(k), dev(v), 0)
+
+    feed_prefill(64)
+    for _ in range(128):
+        feed_decode()                         # the last of these fills the window and starts the asynchronous flush
+    assert cache._pending[0] is not None
+    feed_prefill(64)                          # consumes the pending flush
+    coded = cache.key_cache[0].shape[2]
+    assert coded + cache.residualed_tokens[0] == 64 + 128 + 64 == cache.seen_tokens[0]
+    for _ in range(70):
+        q, out = feed_decode()
+    assert cache.key_cache[0].shape[2] + cache.residualed_tokens[0] == cache.seen_tokens[0] == 64 + 128 + 64 + 70
+    # attention over every token exactly once: the order of KV rows does not matter without a mask
+    K, V = np.concatenate(allk, 2).astype(np.float32), np.concatenate(allv, 2).astype(np.float32)
+    nq = cache.key_cache[0].shape[2]
+    Kc = O.pq_encode(K, kc.astype(np.float32)); Vc = O.pq_encode(V, vc.astype(np.float32))
+    # which tokens are coded: everything except the last `r` decode tokens
+    r = cache.residualed_tokens[0]
+    T = K.shape[2]
+    Kh = np.concatenate([O.pq_decode(Kc[:, :, :T - r], kc.astype(np.float32)), K[:, :, T - r:]], 2)
+    Vh = np.concatenate([O.pq_decode(Vc[:, :, :T - r], vc.astype(np.float32)), V[:, :, T - r:]], 2)
+    s = np.einsum("bhd,bhtd->bht", q[:, :, 0].astype(np.float32), np.repeat(Kh, 4, 1)) / np.sqrt(128)
+    p = np.exp(s - s.max(-1, keepdims=True)); p /= p.sum(-1, keepdims=True)
+    ref = np.einsum("bht,bhtd->bhd", p, np.repeat(Vh, 4, 1))
+    np.testing.assert_allclose(out.float().cpu().numpy()[:, :, 0], ref, atol=ATOL, rtol=RTOL)
+    assert nq == T - r
+
+
+# ------------------------------------------------------------------------------------------------ config 3: paged prefill at 32K
+
+
+def test_paged_prefill_32k_block_table_and_pool_bit_exact():
+    """BASELINE config 3 at full size: PagedPQCache.prefill of 32K tokens (Llama-3.1-8B shapes, one layer): K codes, the block
+    table and every page of the pool bit-exact against the oracle's build_page_pool of the oracle's codes."""
+    from million_b200.paged_pq_utils import PagedPQCache
+    bs, nh, nh_k, T, d = 1, 32, 8, 32768, 128
+    kc, vc = _cents(17)
+    cache = _mk(PagedPQCache, bs=bs, nh=nh, num_key_value_heads=nh_k, M=64, layer_num=1, d=d, scalar_t=torch.float16)
+    cache.set_cent(dev(kc), dev(vc))
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    k = torch.randn(bs, nh_k, T, d, device="cuda", generator=g).half()
+    v = torch.randn(bs, nh_k, T, d, device="cuda", generator=g).half()
+    cache._encode_append(k, v, 0)           # the encode + page write of prefill(), without the 32K x 32K causal SDPA
+    torch.cuda.synchronize()
+    Kc = CO.pq_encode(k.float().cpu().numpy(), kc.astype(np.float32))
+    Vc = CO.pq_encode(v.float().cpu().numpy(), vc.astype(np.float32))
+    assert np.array_equal(cache.key_cache[0].cpu().numpy(), Kc)
+    pool, table = O.build_page_pool(Vc, 64)
+    n_pages = T // 64
+    assert np.array_equal(cache._table[0][:, :, :n_pages].cpu().numpy(), table)
+    assert np.array_equal(cache.page_managers[0].page_pool[:pool.shape[0]].cpu().numpy(), pool)
+    assert np.array_equal(cache.value_cache[0].cpu().numpy(), O.v_codes_transposed(Vc))
+    # and one decode step over those pages against the oracle
+    q = torch.randn(bs, nh, 1, d, device="cuda", generator=g).half()
+    k1, v1 = torch.randn(bs, nh_k, 1, d, device="cuda", generator=g).half(), torch.randn(bs, nh_k, 1, d, device="cuda", generator=g).half()
+    out = cache.decoding_with_pages(q, k1, v1, 0)
+    h = lambda t: t.float().cpu().numpy()
+    ref = CO.pq_decode_attn(h(q), Kc, Vc, kc.astype(np.float32), vc.astype(np.float32),
+                            np.ascontiguousarray(np.pad(h(k1), ((0, 0), (0, 0), (0, 127), (0, 0)))),
+                            np.ascontiguousarray(np.pad(h(v1), ((0, 0), (0, 0), (0, 127), (0, 0)))), 1)
+    _check(out, ref, "paged 32K decode")
+
+
+# ------------------------------------------------------------------------------------------------ config 5: Llama-2-7B (MHA) shapes, outliers
+
+
+@pytest.mark.parametrize("Mm", [64, 32])
+@pytest.mark.parametrize("k_out,v_out", [(0, 0), (2, 0), (2, 2)])
+def test_llama2_7b_mha_shard_with_outlier_store(M, Mm, k_out, v_out):
+    """BASELINE config 5, one rank's share (4 of the 32 MHA heads) at a reduced context: 4-bit (M=64) and 2-bit (M=32) PQ with
+    the outlier side store, against the oracle's A.6 restatement (parity unpinned for the store: the reference has none)."""
+    bs, nh, nk, r, d = 2, 4, 4096 - 100, 100, 128
+    rng = np.random.default_rng(Mm + k_out)
+    f16 = lambda *s: rng.standard_normal(s, dtype=np.float32).astype(np.float16)
+    kcent, vcent = f16(Mm, 256, d // Mm), f16(Mm, 256, d // Mm)
+    K, V = f16(bs, nh, nk, d), f16(bs, nh, nk, d)
+    heavy = rng.random(K.shape) < 0.01
+    K = np.where(heavy, K * 20, K).astype(np.float16)     # 1 % of entries scaled x20
+    V = np.where(rng.random(V.shape) < 0.01, V * 20, V).astype(np.float16)
+    q, kres, vres = f16(bs, nh, 1, d), f16(bs, nh, 128, d), f16(bs, nh, 128, d)
+    cf = lambda a: a.astype(np.float32)
+    if k_out:
+        kc_, ki, kv = M.pq_encode_outliers(dev(K), dev(cf(kcent)), k_out)
+        okc, oki, okv = O.pq_encode_outliers(cf(K), cf(kcent), k_out)
+        assert np.array_equal(kc_.cpu().numpy(), okc) and np.array_equal(ki.cpu().numpy(), oki)
+        assert np.array_equal(kv.float().cpu().numpy(), np.asarray(okv, dtype=np.float32))
+    else:
+        kc_ = M.pq_encode(dev(K), dev(cf(kcent))); okc = O.pq_encode(cf(K), cf(kcent)); ki = kv = oki = okv = None
+        assert np.array_equal(kc_.cpu().numpy(), okc)
+    if v_out:
+        vc_, vi, vv = M.pq_encode_outliers(dev(V), dev(cf(vcent)), v_out)
+        ovc, ovi, ovv = O.pq_encode_outliers(cf(V), cf(vcent), v_out)
+        assert np.array_equal(vc_.cpu().numpy(), ovc) and np.array_equal(vi.cpu().numpy(), ovi)
+    else:
+        vc_ = M.pq_encode(dev(V), dev(cf(vcent))); ovc = O.pq_encode(cf(V), cf(vcent)); vi = vv = ovi = ovv = None
+        assert np.array_equal(vc_.cpu().numpy(), ovc)
+    out = M.pq_decode_attn(dev(q), kc_, vc_, dev(kcent), dev(vcent), dev(kres), dev(vres), r,
+                           k_outliers=(ki, kv) if k_out else None, v_outliers=(vi, vv) if v_out else None)
+    ref = O.pq_decode_attn_outliers(cf(q), okc, ovc, cf(kcent), cf(vcent), cf(kres), cf(vres), r,
+                                    kout=(oki, cf(okv)) if k_out else None, vout=(ovi, cf(ovv)) if v_out else None)
+    _check(out, ref, f"7B shard M={Mm} outliers=({k_out},{v_out})")
+
+
+# ------------------------------------------------------------------------------------------------ C ABI: encoder choice, device list
+
+
+def test_c_abi_auto_encoder_picks_the_grid_encoder(M):
+    """A non-Python host gets the fast exact encoder from impl = AUTO: million_pq_encoder_auto_prepare builds the tables AUTO
+    wants for the shape, and the codes are the exact encoder's."""
+    from million_b200 import _lib as L
+    lib = L.lib()
+    g = torch.Generator(device="cuda"); g.manual_seed(8)
+    for Mm in (64, 32):
+        X = torch.randn(2, 8, 1000, 128, device="cuda", generator=g).half()
+        cent = torch.randn(Mm, 256, 128 // Mm, device="cuda", generator=g).half().float().contiguous()
+        nbytes = lib.million_pq_encoder_auto_prepared_bytes(128, Mm, 256)
+        assert nbytes > 0 and (Mm != 64 or nbytes == lib.million_pq_encoder_grid_prepared_bytes(128, Mm, 256))
+        prep = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        L.check(lib.million_pq_encoder_auto_prepare(p(cent), L.MILLION_F16, 128, Mm, 256, p(prep), s))
+        codes = torch.empty(2, 8, 1000, Mm, dtype=torch.uint8, device="cuda")
+        L.check(lib.million_pq_encode(p(X), L.MILLION_F16, 1000 * 128, p(cent), p(prep), p(codes), 1, 1000 * Mm, Mm, 1, 0, 16, 1000, 128, Mm, 256,
+                                      L.IMPL_AUTO, s))
+        assert torch.equal(codes, M.pq_encode(X, cent, impl=L.IMPL_GENERIC))
+
+
+def test_debug_hooks_are_not_in_the_product_build():
+    from million_b200 import _lib as L
+    with pytest.raises(AttributeError):     # ctypes resolves symbols on attribute access
+        getattr(L.lib(), "million_debug_set_mode")
