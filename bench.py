@@ -259,7 +259,7 @@ def build_layers(torch, bs, nh, nh_k, nk, device, n_layers, m=M, k_out=0, seed=4
     return kcent, vcent, layers
 
 
-def resident_graph(torch, ops, bs, nh, nh_k, nk, r, device, impl=0, k_out=0, m=M, n_buffers=LAYERS, n_launch=LAYERS):
+def resident_graph(torch, ops, bs, nh, nh_k, nk, r, device, impl=0, k_out=0, m=M, n_buffers=LAYERS, n_launch=LAYERS, pdl=True):
     """CUDA graph of one n_launch-layer step over n_buffers distinct resident layer caches."""
     kcent, vcent, layers = build_layers(torch, bs, nh, nh_k, nk, device, n_buffers, m=m, k_out=k_out)
     ws = ops.attn_workspace(device, bs, nh, nh_k, D, ops.default_splits(bs, nh_k, nk))
@@ -268,7 +268,7 @@ def resident_graph(torch, ops, bs, nh, nh_k, nk, r, device, impl=0, k_out=0, m=M
         for i in range(n_launch):
             L_ = layers[i % n_buffers]
             ops.pq_decode_attn(L_["q"], L_["kc"], L_["vc"], kcent, vcent, L_["kres"], L_["vres"], r, out=L_["out"], workspace=ws, impl=impl,
-                               k_outliers=L_["ko"])
+                               k_outliers=L_["ko"], pdl=pdl)
 
     return capture(torch, step), layers, (kcent, vcent)
 
@@ -379,22 +379,36 @@ def splitkv_128k(torch, dist, ops, T, world, rank, device, peak, steps):
         local = [(torch.randint(0, C, (1, NH_K, e - s, M), dtype=torch.uint8, device=device), torch.randint(0, C, (1, NH_K, e - s, M), dtype=torch.uint8, device=device))
                  for _ in range(n_buf)]
         out = torch.empty(1, NH, 1, D, dtype=torch.float16, device=device)
-
-        def step():
-            for k_, v_ in local:
-                peer.decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, out=out)
-
-        graph = capture(torch, step, warm=2)
-        for _ in range(3):
-            graph.replay()
-        secs = T.run(graph.replay, steps)
+        variants = {}
+        for name, fused, pdl in (("two_launches", False, False), ("two_launches_pdl", False, True), ("fused", True, False), ("fused_pdl", True, True)):
+            def step():
+                for k_, v_ in local:
+                    peer.decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, out=out, fused=fused, pdl=pdl)
+            try:
+                chk = peer.decode_attn(q, kc_full[:, :, s:e].contiguous(), vc_full[:, :, s:e].contiguous(), kcent, vcent, kres, vres, r_local, fused=fused, pdl=pdl)
+                verr = torch.tensor([(chk.float() - single.float()).abs().max().item()], device=device)
+                dist.all_reduce(verr, op=dist.ReduceOp.MAX)
+                graph = capture(torch, step, warm=2)
+                for _ in range(3):
+                    graph.replay()
+                secs = T.run(graph.replay, steps)
+                variants[name] = {"ms_per_token": secs / steps * 1e3, "us_per_layer": secs / steps / LAYERS * 1e6, "max_abs_vs_single_gpu": float(verr.item())}
+                del graph
+            except Exception as ex:       # e.g. a shape the fused exchange is not compiled for
+                variants[name] = {"error": repr(ex)[:200]}
         timed_out = torch.tensor([1.0 if peer.timed_out() else 0.0], device=device)
         dist.all_reduce(timed_out, op=dist.ReduceOp.MAX)
-        res.update({"ms_per_token": secs / steps * 1e3, "tokens_per_s": steps / secs, "us_per_layer": secs / steps / LAYERS * 1e6,
-                    "frac_of_hbm_roofline_per_gpu": alg / world / (secs / steps / LAYERS) / 1e9 / peak,
-                    "exchange": "million_splitkv_push_merge (NVLink peer stores + flags), 2 launches per layer, one CUDA graph per step",
+        ok = {k: v for k, v in variants.items() if "ms_per_token" in v}
+        best = min(ok, key=lambda k: ok[k]["ms_per_token"])
+        secs_step = ok[best]["ms_per_token"] / 1e3
+        res.update({"ms_per_token": secs_step * 1e3, "tokens_per_s": 1.0 / secs_step, "us_per_layer": secs_step / LAYERS * 1e6,
+                    "frac_of_hbm_roofline_per_gpu": alg / world / (secs_step / LAYERS) / 1e9 / peak, "exchange": best,
+                    "exchange_variants": variants,
+                    "exchange_note": "two_launches = attention (PARTIAL_ONLY) + million_splitkv_push_merge; fused = per-group exchange inside the attention "
+                                     "kernel's merge epilogue (NVLink peer stores + per-(rank, group) flags); pdl = programmatic dependent launch; "
+                                     "each variant is one CUDA graph per 32-layer step",
                     "exchange_timed_out": bool(timed_out.item())})
-        del graph, local, peer
+        del local, peer
     # the 1-GPU number of the same run (rank 0; the others wait at the barrier)
     one = None
     if rank == 0:
@@ -471,12 +485,15 @@ def paged_prefill_async(torch, device):
         cache = PagedPQCache(bs=1, nh=NH, num_key_value_heads=NH_K, M=M, layer_num=LAYERS, d=D, scalar_t=torch.float16, async_flush=async_flush, device=device)
         cache.set_cent(ck, cv)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record()
-        for l in range(LAYERS):
-            cache._encode_append(k0, v0, l)           # the quantize-and-page part of prefill() (its SDPA is library code)
-        e1.record(); torch.cuda.synchronize()
+        for attempt in range(2):                       # the first pass pays cudaMalloc for the pools (allocator warm-up), the second is timed
+            if attempt:
+                cache.cleanup()
+            torch.cuda.synchronize(); e0.record()
+            for l in range(LAYERS):
+                cache._encode_append(k0, v0, l)       # the quantize-and-page part of prefill() (its SDPA is library code)
+            e1.record(); torch.cuda.synchronize()
         prefill_ms = e0.elapsed_time(e1)
-        for _ in range(70):                            # warm-up across the first flush
+        for _ in range(140):                           # warm-up across the first two flushes (page-pool growth, lazy kernel loading)
             for l in range(LAYERS):
                 cache.decoding_with_pages(qs[l], ks[l], vs[l], l)
         torch.cuda.synchronize()
@@ -508,6 +525,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline + e2e only")
+    ap.add_argument("--pdl", type=int, default=1, help="1: launch with programmatic dependent launch (MILLION_ATTN_PDL), 0: plain launches")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -554,7 +572,7 @@ def main():
     peak, peak_src = measured_peaks()
 
     # ---- resident-inputs number (value) + roofline
-    graph, layers, cents = resident_graph(torch, ops, bs_g, nh_l, nhk_l, nk, r, device, impl=args.kernel)
+    graph, layers, cents = resident_graph(torch, ops, bs_g, nh_l, nhk_l, nk, r, device, impl=args.kernel, pdl=bool(args.pdl))
     for _ in range(warmup):
         graph.replay()
     with ClockSampler(local) as clk:
@@ -576,7 +594,7 @@ def main():
     if not args.no_extras:
         if rank == 0:
             def bs1():
-                g1, l1, c1 = resident_graph(torch, ops, 1, NH, NH_K, nk, r, device, impl=args.kernel)
+                g1, l1, c1 = resident_graph(torch, ops, 1, NH, NH_K, nk, r, device, impl=args.kernel, pdl=bool(args.pdl))
                 for _ in range(warmup):
                     g1.replay()
                 s1 = T.run(g1.replay, steps, sync_ranks=False)
@@ -643,7 +661,7 @@ def main():
         cfg = workload_config(args, world)
         cfg.update({"sharding": (f"by KV head, no collective: rank g owns kv-heads [g*{nhk_l}, (g+1)*{nhk_l}) and their {nh_l} query heads of a "
                                  f"global batch of {bs_g} sequences" if world > 1 else "single GPU"),
-                    "l2": f"inputs larger than L2: {LAYERS} layer caches, {LAYERS * alg / 1e9:.2f} GB touched per step per GPU", "kernel": args.kernel})
+                    "l2": f"inputs larger than L2: {LAYERS} layer caches, {LAYERS * alg / 1e9:.2f} GB touched per step per GPU", "kernel": args.kernel, "launch": "CUDA graph of 32 launches, programmatic dependent launch" if args.pdl else "CUDA graph of 32 plain launches"})
         line = {
             "metric": "pq_decode_attn_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",

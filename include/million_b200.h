@@ -170,7 +170,7 @@ typedef struct million_attn_params {
     int32_t r;  /* valid residual rows, 0 <= r <= res_len (the reference requires r > 0) */
 
     const void* q; /* (bs, nh, d) — the reference's (bs, nh, 1, d) */
-    const uint8_t* k_codes; /* (bs, nh_k, nk, M) row-major */
+    const uint8_t* k_codes; /* (bs, nh_k, nk, M) row-major, uint8 (or uint16: code_bytes = 2) */
     int64_t k_head_stride;  /* BYTES between consecutive (b, hk) blocks (>= nk*M; lets a preallocated cache be used) */
 
     int32_t v_layout;       /* million_v_layout */
@@ -218,11 +218,12 @@ typedef struct million_attn_params {
     int64_t v_out_head_stride;
 
     /* Split-KV across GPUs fused into this launch (MILLION_ATTN_FUSED_SPLITKV): instead of returning the rank's partial state,
-     * the last CTA of every (b, kv-head) group stores it straight into every peer's symmetric buffer over NVLink, the last
-     * group publishes this rank's sequence flag, waits for the flags of all ranks (bounded spin) and writes the merged
-     * result to `out`.  Same buffers and protocol as million_splitkv_push_merge (rows = bs * nh); `p2p_state` is the
-     * million_splitkv_state_bytes() block prepared once by million_splitkv_state_init.  EXPERIMENTAL: compiled only with
-     * -DMILLION_FUSED_SPLITKV (slower than the separate exchange launch so far); other builds return MILLION_ERR_UNSUPPORTED. */
+     * the last CTA of every (b, kv-head) group stores the group's rows straight into every peer's symmetric buffer over NVLink,
+     * publishes a per-(rank, group) sequence flag, waits for the peers' flags of ITS group (bounded spin) and writes the merged
+     * rows to `out` — one launch per layer, no cross-group serialisation.  Same buffers as million_splitkv_push_merge
+     * (rows = bs * nh); `p2p_state` is the million_splitkv_state_bytes() block prepared once by million_splitkv_state_init.
+     * Compiled for the fast kernel at M = 64, nh/nh_k = 4, row-major value codes, no side store; MILLION_ERR_UNSUPPORTED otherwise.
+     * If a wait gives up (dead peer), the affected rows are NaN and the error word of the state block is set. */
     void* p2p_state;
 
     /* Window append fused into the attention launch (pq_utils.py:304-311 followed by :313-327, one launch instead of a copy
@@ -236,12 +237,22 @@ typedef struct million_attn_params {
      * launch with k_new/v_new and r = 1 means "append at row *r_dev, attend over *r_dev + 1 rows".  Bump the counter after the
      * last layer of a step with million_counter_add.  Host-side checks on r then apply to the offset only. */
     const int32_t* r_dev;
+    /* Width of the codes in k_codes / v_codes / the page pool: 0 or 1 = uint8 (C <= 256), 2 = uint16 (the reference's
+     * nbits2dtype for nbits > 8, pq_utils.py:542-552; C <= 65536).  Strides stay in BYTES.  Two-byte codes run on the all-shapes
+     * kernel (the reference compiles no kernel for them at all: pq_utils.py:58-59). */
+    int32_t code_bytes;
+    int32_t reserved0;
 } million_attn_params;
 
 #define MILLION_MAX_OUTLIERS 8
 
 #define MILLION_ATTN_PARTIAL_ONLY 1
 #define MILLION_ATTN_FUSED_SPLITKV 2
+/* Programmatic dependent launch: the kernel may start while its stream predecessor drains — table copies and the first code
+ * tiles are requested at once, everything else (q, k_new/v_new, the window, the workspace, r_dev) is read after the
+ * predecessor has completed.  Requirement: the predecessor does not WRITE k_codes / v_codes / page table / prepared_codebook
+ * / outlier stores of this call.  Capturable in CUDA graphs. */
+#define MILLION_ATTN_PDL 4
 
 /* Codebook preparation for the FAST decode-attention kernel: both codebooks as fp16 pairs in the kernel's gather
  * order (d=128, M in {32, 64}, C=256 only: returns 0 bytes / MILLION_ERR_UNSUPPORTED otherwise).  One tiny launch; callers
@@ -264,16 +275,21 @@ int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, vo
  * peer's symmetric buffer (NVLink P2P stores), publishes a flag, waits for all sources and merges — one launch, graph
  * capturable.  `peer_bases_host`: host array of `world` device pointers, the symmetric buffers of all ranks mapped into
  * this process (e.g. torch.distributed._symmetric_memory buffer_ptrs), each million_splitkv_symmetric_bytes() big and
- * zero-initialised once.  `state`: 16 bytes of zero-initialised device memory private to this rank. */
+ * zero-initialised once.  `state`: 16 bytes of zero-initialised device memory private to this rank (or the block of
+ * million_splitkv_state_init).  rows <= 512: every block of the kernel waits for the peers, so the grid must be co-resident.
+ * flags: 0 or MILLION_ATTN_PDL (`local_partial` is read after the stream predecessor has completed).
+ * A wait that gives up (default ~0.8 s, million_splitkv_set_timeout) writes NaN rows and sets the error word state[2]. */
 int64_t million_splitkv_symmetric_bytes(int world, int64_t rows, int d);
-/* Protocol state of one rank: [calls completed u32 | ticket i32 | error i32 | pad | rank i32 | world i32 | rows i32 | pad | peer pointers x 8].
+/* Protocol state of one rank: [calls completed u32 | ticket i32 | error i32 | spin limit i32 | rank i32 | world i32 | rows i32 | pad | peer pointers x 8].
  * million_splitkv_state_init zeroes it and records rank, world, rows (= bs * nh of the calls it will serve) and the peers'
  * symmetric buffers (asynchronous on `stream`);
  * million_splitkv_push_merge only needs its first 16 bytes. */
 int64_t million_splitkv_state_bytes(void);
 int million_splitkv_state_init(void* state, void* const* peer_bases_host, int rank, int world, int64_t rows, million_stream_t stream);
+/* how long a wait for the peers may last before it gives up (0 = the default) */
+int million_splitkv_set_timeout(void* state, int64_t microseconds, million_stream_t stream);
 int million_splitkv_push_merge(const float* local_partial, void* const* peer_bases_host, int rank, int world, int64_t rows, int d,
-                               void* out, int io_dtype, void* state, million_stream_t stream);
+                               void* out, int io_dtype, void* state, int flags, million_stream_t stream);
 
 /* window[(head), r0 + i, :] = src[(head), i, :] for i < n — pq_utils.py:304-311, paged_pq_utils.py:377-378.
  * Both K and V in one launch.  Strides in ELEMENTS. */

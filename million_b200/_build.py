@@ -29,7 +29,7 @@ def _digest():
     h = hashlib.sha256()
     files = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "million_b200.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())     # names, not absolute paths: the stamp must hold on the GPU box's copy of the tree
         h.update(open(f, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -15,6 +15,7 @@ V_ROWMAJOR, V_TRANSPOSED, V_PAGED = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_FAST, IMPL_GRID = 0, 1, 2, 3
 ATTN_PARTIAL_ONLY = 1
 ATTN_FUSED_SPLITKV = 2
+ATTN_PDL = 4
 ABI_VERSION = 7
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
@@ -43,6 +44,7 @@ class AttnParams(ctypes.Structure):
         ("v_out_idx", c_vp), ("v_out_val", c_vp), ("v_out_head_stride", c_i64),
         ("p2p_state", c_vp),
         ("k_new", c_vp), ("v_new", c_vp), ("r_dev", c_vp),
+        ("code_bytes", c_i32), ("reserved0", c_i32),
     ]
 
 
@@ -76,7 +78,8 @@ SIGNATURES = {
     "million_splitkv_symmetric_bytes": (c_i64, [ctypes.c_int, c_i64, ctypes.c_int]),
     "million_splitkv_state_bytes": (c_i64, []),
     "million_splitkv_state_init": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, c_vp]),
-    "million_splitkv_push_merge": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp]),
+    "million_splitkv_set_timeout": (ctypes.c_int, [c_vp, c_i64, c_vp]),
+    "million_splitkv_push_merge": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
     "million_window_append": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, c_vp]),
     "million_counter_add": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),

@@ -16,8 +16,7 @@ struct AttnArgs {
     const void* k_res;
     const void* v_res;
     void* out;
-    float* partial_out;   // PARTIAL_ONLY target or nullptr; with bit 0 set: the P2PState block of the fused split-KV exchange
-                          // (tagged pointer on purpose: one more kernel parameter measurably perturbs the main loop's allocation)
+    float* partial_out;   // PARTIAL_ONLY target or nullptr; the P2PState block in the fused split-KV instantiations (P2P = true)
     int* counters;        // (bs*nh_k) arrival tickets, zero on entry and on exit
     float* parts;         // (bs*nh, n_parts, d+2) fp32: [o_unnormalised | m (log2 units) | l]
     int64_t k_head_stride, v_head_stride, v_ld;
@@ -37,6 +36,10 @@ struct AttnArgs {
     // fused window append: the new token's key/value (bs, nh_k, d), stored into window row r-1 by the CTA that owns that row
     const void* k_new; const void* v_new;
     const int* r_dev;                 // device-resident window length: r = min(*r_dev + r, res_len) (graph replay), or nullptr
+    int code_bytes;                   // 1: uint8 codes (C <= 256); 2: uint16 codes (nbits2dtype for nbits > 8, C <= 65536) — generic kernel only
+    int direct;                       // generic kernel: the M x C LUT does not fit shared memory, scores come from the centroids
+    int pdl;                          // host only: launch with the programmatic-serialization attribute (MILLION_ATTN_PDL)
+    int p2p;                          // host only: fused split-KV instantiation (partial_out = P2PState)
 #ifdef MILLION_DEBUG
     int dbg_mode;                     // ablation switch (million_debug_set_mode): bit 0 skips QK gathers, bit 1 skips PV, bit 2 tile loads
     unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 64 words per CTA, see dbg_stamp
@@ -76,12 +79,20 @@ __device__ __forceinline__ void split_range(const AttnArgs& a, int s, int& begin
     end = (int)(e < a.nk ? e : a.nk);
 }
 
+// code at BYTE offset `base` + element index `idx` of a one- or two-byte code array (strides of the ABI are in bytes)
+__device__ __forceinline__ int code_load(const uint8_t* p, int64_t base, int64_t idx, int code_bytes) {
+    return code_bytes == 2 ? (int)reinterpret_cast<const uint16_t*>(p + base)[idx] : (int)p[base + idx];
+}
+// K code of token j, sub-space m (row-major)
+__device__ __forceinline__ int k_code_at(const AttnArgs& a, int hb, int j, int m) {
+    return code_load(a.k_codes, hb * a.k_head_stride, (int64_t)j * a.M + m, a.code_bytes);
+}
 // V code of token j, sub-space m for head block hb = b*nh_k + hk  (generic path; the fast path stages tiles)
 __device__ __forceinline__ int v_code_at(const AttnArgs& a, int hb, int j, int m) {
-    if (a.v_layout == MILLION_V_ROWMAJOR) return a.v_codes[hb * a.v_head_stride + (int64_t)j * a.M + m];
-    if (a.v_layout == MILLION_V_TRANSPOSED) return a.v_codes[hb * a.v_head_stride + (int64_t)m * a.v_ld + j];
+    if (a.v_layout == MILLION_V_ROWMAJOR) return code_load(a.v_codes, hb * a.v_head_stride, (int64_t)j * a.M + m, a.code_bytes);
+    if (a.v_layout == MILLION_V_TRANSPOSED) return code_load(a.v_codes, hb * a.v_head_stride + (int64_t)m * a.v_ld, j, a.code_bytes);
     const int64_t page = a.v_page_ids[(int64_t)hb * a.n_pages + j / a.page_size];
-    return a.v_codes[(page * a.M + m) * a.page_size + (j % a.page_size)];
+    return code_load(a.v_codes, 0, (page * a.M + m) * a.page_size + (j % a.page_size), a.code_bytes);
 }
 
 // Merge the first n_parts partial states of every query head of group (b, hk) and write the result.
@@ -103,12 +114,19 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Symmetric buffer of the split-KV exchange (same layout on every rank; million_splitkv_symmetric_bytes):
+//   [0, 1024)            per-source-rank flags of million_splitkv_push_merge: rank g at byte 128*g (u32 sequence number)
+//   [1024, 1024 + 8192)  per-(source rank, group) flags of the exchange fused into the attention kernel: u32 at (g*256 + group)*4
+//   [9216, ...)          recv[parity 2][world][rows][d+2] fp32
+constexpr int kP2PGroupFlagOff = 1024, kP2PMaxGroups = 256, kP2PRecvOff = 1024 + 8 * kP2PMaxGroups * 4;
+
 // device-memory block of the split-KV protocol (million_splitkv_state_init): read only on the merge path
 struct P2PState {
-    unsigned counter; int ticket; int err; int pad0;
+    unsigned counter; int ticket; int err; int spin_limit;   // spin_limit: polls (100 ns apart) before a wait gives up; 0 = default
     int rank, world, rows, pad1;     // rows = bs * nh of the calls this block is used with
     unsigned char* peer[8];
 };
+constexpr int kP2PDefaultSpins = 1 << 23;    // ~0.8 s
 
 struct MergeArgs {
     int nh, nh_k, n_parts, d;
@@ -130,24 +148,22 @@ __device__ __forceinline__ void dbg_stamp_m(const MergeArgs&, int) {}
 #endif
 // Out of line on purpose: it runs once per group, and inlined into the attention kernels its registers and code perturb the
 // allocation and layout of their main loops (measured: +7 us per launch at batch 8 for the same loop rate).
-template <typename T>
+// P2P = true (split-KV across GPUs fused into the attention launch, MILLION_ATTN_FUSED_SPLITKV): a.partial_out is the P2PState
+// block; the merged rows of THIS group go straight into every peer's receive buffer, a per-(rank, group) flag is published, and
+// the same CTA waits for the peers' flags of its group and writes the final rows — no cross-group ticket on the critical path,
+// no second launch.  A separate instantiation on purpose: code in the plain merge perturbs the attention kernels that call it
+// (measured in round 1: +2.5 % per launch at batch 8).
+template <typename T, bool P2P>
 __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, int n_parts, float* scr) {
     const int G = a.nh / a.nh_k;
-    // Compiled in only with -DMILLION_FUSED_SPLITKV: the mere presence of this path in the (out-of-line) merge function changes the
-    // register allocation of the attention kernels that call it and costs 2.5 % per launch at batch 8 (107.4 vs 104.8 us, A/B on
-    // one box), while the fused exchange itself is slower than the separate exchange launch.
-#ifdef MILLION_FUSED_SPLITKV
-    const bool p2p = (reinterpret_cast<uintptr_t>(a.partial_out) & 1) != 0;
-#else
-    const bool p2p = false;
-#endif
-    P2PState* const ps = reinterpret_cast<P2PState*>(reinterpret_cast<uintptr_t>(a.partial_out) & ~(uintptr_t)1);
+    constexpr bool p2p = P2P;
+    P2PState* const ps = reinterpret_cast<P2PState*>(a.partial_out);
     unsigned p2p_seq = 0, p2p_par = 0;
     int p2p_rank = 0, p2p_world = 0, p2p_rows = 0;
     size_t p2p_slot = 0;
-    if (p2p) {
+    if constexpr (P2P) {
         p2p_rows = ps->rows;
-        p2p_slot = (size_t)p2p_rows * (a.d + 2);   // the counter moves only after every group of this launch has pushed: all group-last CTAs read the same value
+        p2p_slot = (size_t)p2p_rows * (a.d + 2);   // the counter moves only after every group of this launch is done: all group-last CTAs read the same value
         p2p_seq = *reinterpret_cast<volatile unsigned*>(&ps->counter) + 1;
         p2p_par = p2p_seq & 1;
         p2p_rank = ps->rank; p2p_world = ps->world;
@@ -266,12 +282,12 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
                 for (; i < n_parts; ++i) acc = fmaf(__ldcg(src + (int64_t)i * stride), w[i], acc);
             }
             const int h = h0 + g;
-            if (p2p) {
+            if constexpr (P2P) {
                 // fused split-KV: this rank's state of row (b, h) goes straight into slot [parity][rank] of EVERY rank's receive
                 // buffer (NVLink stores, consecutive k = coalesced); layout of million_splitkv_push_merge
                 const size_t off = ((size_t)p2p_par * p2p_world + p2p_rank) * p2p_slot + (size_t)(b * a.nh + h) * ostride;
                 for (int r = 0; r < p2p_world; ++r) {
-                    float* dst = reinterpret_cast<float*>(ps->peer[r] + 1024) + off;
+                    float* dst = reinterpret_cast<float*>(ps->peer[r] + kP2PRecvOff) + off;
                     dst[k] = acc;
                     if (k == 0) { dst[a.d] = hd[2 * g] * kLn2; dst[a.d + 1] = hd[2 * g + 1]; }
                 }
@@ -288,82 +304,77 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
         }
         __syncthreads();
     }
-    if (!p2p) return;
-    // ---------------------------------------------------------------- fused split-KV: publish, wait for the peers, final merge
-    // Ordering as in splitkv_p2p.cu: this block's peer stores -> bar.sync -> acq_rel ticket at gpu scope -> (the last group's
-    // block) release stores of the flags at system scope -> the peers' acquire loads.
-    int* sflag = reinterpret_cast<int*>(scr);
-    if (threadIdx.x == 0) {
-        int t;
-        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(&ps->ticket) : "memory");
-        const int last = (t == p2p_rows / G - 1);     // groups = rows / (nh / nh_k)
-        if (last) {
-            ps->ticket = 0;
-            *reinterpret_cast<volatile unsigned*>(&ps->counter) = p2p_seq;
-        }
-        *sflag = last;
-    }
-    __syncthreads();
-    if (!*sflag) return;
-    if ((int)threadIdx.x < p2p_world) {
-        st_release_sys(reinterpret_cast<unsigned*>(ps->peer[threadIdx.x] + 128 * p2p_rank), p2p_seq);   // every group of this rank has pushed
-        const unsigned* f = reinterpret_cast<const unsigned*>(ps->peer[p2p_rank] + 128 * threadIdx.x);
-        int spins = 0;
-        while ((int)(ld_acquire_sys(f) - p2p_seq) < 0) {      // bounded: a dead peer must not hang the GPU
-            __nanosleep(100);
-            if (++spins > (1 << 23)) { ps->err = 1; break; }
-        }
-    }
-    __syncthreads();
-    // final merge of rows x world parts by this one block, arranged so that every phase is ONE round of independent L2 loads:
-    // (1) all (m, l) pairs, (2) weights per row, (3) the outputs, 4 x world loads in flight per thread
-    const float* recv = reinterpret_cast<const float*>(ps->peer[p2p_rank] + 1024) + (size_t)p2p_par * p2p_world * p2p_slot;
-    const int W = p2p_world, os = a.d + 2;
-    float* sm_m = scr;                 // [rows][W]   (rows * W <= 2048 is checked on the host: rows <= 256)
-    float* sm_l = scr + 2048;          // [rows][W]
-    float* sm_w = scr + 4096;          // [rows][W] weights / den
-    for (int i = threadIdx.x; i < p2p_rows * W; i += blockDim.x) {
-        const int row = i / W, g = i - row * W;
-        const float* p = recv + (size_t)g * p2p_slot + (size_t)row * os;
-        sm_m[i] = __ldcg(p + a.d);
-        sm_l[i] = __ldcg(p + a.d + 1);
-    }
-    __syncthreads();
-    for (int row = threadIdx.x; row < p2p_rows; row += blockDim.x) {
-        float mstar = -INFINITY, den = 0.f;
-        for (int g = 0; g < W; ++g)
-            if (sm_l[row * W + g] > 0.f) mstar = fmaxf(mstar, sm_m[row * W + g]);
-        for (int g = 0; g < W; ++g) {
-            const float l = sm_l[row * W + g];
-            const float w = l > 0.f ? __expf(sm_m[row * W + g] - mstar) : 0.f;
-            sm_w[row * W + g] = w;
-            den += l * w;
-        }
-        const float inv = den > 0.f ? 1.f / den : 0.f;
-        for (int g = 0; g < W; ++g) sm_w[row * W + g] *= inv;
-    }
-    __syncthreads();
-    const int total = p2p_rows * a.d;
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * blockDim.x;
-            if (i < total) {
-                const int row = i / a.d, k = i - row * a.d;
-                const float* p = recv + (size_t)row * os + k;
-                for (int g = 0; g < W; ++g) acc[u] = fmaf(__ldcg(p + (size_t)g * p2p_slot), sm_w[row * W + g], acc[u]);
+    if constexpr (P2P) {
+        // ---------------------------------------------------------------- publish this group, wait for the peers' rows of it, final merge
+        // Ordering: the block's peer stores -> bar.sync -> release stores of the group flag at system scope (one thread per
+        // destination; release is cumulative over what the barrier ordered before it) -> the peers' acquire loads.
+        const int grp = b * a.nh_k + hk;
+        __syncthreads();
+        int* sflag = reinterpret_cast<int*>(scr);
+        if (threadIdx.x == 0) *sflag = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < p2p_world) {
+            st_release_sys(reinterpret_cast<unsigned*>(ps->peer[threadIdx.x] + kP2PGroupFlagOff) + p2p_rank * kP2PMaxGroups + grp, p2p_seq);
+            const unsigned* f = reinterpret_cast<const unsigned*>(ps->peer[p2p_rank] + kP2PGroupFlagOff) + threadIdx.x * kP2PMaxGroups + grp;
+            const int limit = ps->spin_limit > 0 ? ps->spin_limit : kP2PDefaultSpins;
+            int spins = 0;
+            while ((int)(ld_acquire_sys(f) - p2p_seq) < 0) {      // bounded: a dead peer must not hang the GPU
+                __nanosleep(100);
+                if (++spins > limit) { ps->err = 1; *sflag = 1; break; }
             }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * blockDim.x;
-            if (i < total) reinterpret_cast<T*>(a.out)[i] = io<T>::from_f(acc[u]);
+        __syncthreads();
+        const bool timed_out = *sflag != 0;
+        // G rows x world parts, all from this rank's own receive buffer: (1) the (m, l) pairs, (2) weights, (3) outputs
+        const float* recv = reinterpret_cast<const float*>(ps->peer[p2p_rank] + kP2PRecvOff) + (size_t)p2p_par * p2p_world * p2p_slot;
+        const int W = p2p_world, os = a.d + 2, row0 = b * a.nh + hk * G;
+        float* sm_m = scr + 64;            // [G][W]   (G * W <= 8 * 64 fits the 2048-float blocks with room to spare)
+        float* sm_l = scr + 2048;
+        float* sm_w = scr + 4096;
+        for (int i = threadIdx.x; i < G * W; i += blockDim.x) {
+            const int g = i / W, w = i - g * W;
+            const float* p = recv + (size_t)w * p2p_slot + (size_t)(row0 + g) * os;
+            sm_m[i] = __ldcg(p + a.d);
+            sm_l[i] = __ldcg(p + a.d + 1);
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            float mstar = -INFINITY, den = 0.f;
+            for (int w = 0; w < W; ++w)
+                if (sm_l[g * W + w] > 0.f) mstar = fmaxf(mstar, sm_m[g * W + w]);
+            for (int w = 0; w < W; ++w) {
+                const float l = sm_l[g * W + w];
+                const float wt = l > 0.f ? __expf(sm_m[g * W + w] - mstar) : 0.f;
+                sm_w[g * W + w] = wt;
+                den += l * wt;
+            }
+            const float inv = den > 0.f ? 1.f / den : 0.f;
+            for (int w = 0; w < W; ++w) sm_w[g * W + w] *= inv;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < G * a.d; i += blockDim.x) {
+            const int g = i / a.d, k = i - g * a.d;
+            const float* p = recv + (size_t)(row0 + g) * os + k;
+            float acc = 0.f;
+            for (int w = 0; w < W; ++w) acc = fmaf(__ldcg(p + (size_t)w * p2p_slot), sm_w[g * W + w], acc);
+            // a wait that gave up must not pass stale rows on as a result: poison them (and P2PState.err is set)
+            reinterpret_cast<T*>(a.out)[(size_t)(row0 + g) * a.d + k] = io<T>::from_f(timed_out ? __int_as_float(0x7fc00000) : acc);
+        }
+        // off the critical path: the last group of the launch advances the call counter (every group-last CTA of the NEXT launch
+        // reads it after that launch's dependency on this one is resolved)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t;
+            asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(&ps->ticket) : "memory");
+            if (t == p2p_rows / G - 1) {              // groups = rows / (nh / nh_k)
+                ps->ticket = 0;
+                *reinterpret_cast<volatile unsigned*>(&ps->counter) = p2p_seq;
+            }
         }
     }
 }
 
-template <typename T>
+template <typename T, bool P2P = false>
 __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, int n_parts, float* scr, float* big = nullptr, int big_floats = 0, unsigned long long* bar = nullptr, int dbg_piece = 0) {
     MergeArgs m;
     m.bar = bar;
@@ -372,7 +383,7 @@ __device__ __forceinline__ void merge_group(const AttnArgs& a, int b, int hk, in
 #ifdef MILLION_DEBUG
     m.dbg_piece = dbg_piece; m.dbg_timing = a.dbg_timing;
 #endif
-    merge_group_impl<T>(m, b, hk, n_parts, scr);
+    merge_group_impl<T, P2P>(m, b, hk, n_parts, scr);
 }
 
 // Arrival ticket: returns true in every thread of the LAST CTA of group `grp` (of `expected` CTAs).

@@ -50,8 +50,13 @@ int launch_codebook_prepare(const void* kcent, const void* vcent, int io_dtype, 
 
 // One segment = the coded tokens [t0, t1) of group (b, hk) (+ this CTA's share of the window), written as part `split` of
 // `np` parts of that group.
-// OUT = 1: K-side outlier records (a.k_out <= 4 per token) are added to the scores; OUT = 0 is the plain path, untouched.
-template <typename T, int G, int VL, int OUT>
+// OUT bit 0: K-side outlier records (a.k_out <= 4 per token) are added to the scores.  OUT bit 1 (G <= 2 only: the G = 4 kernel
+// has no shared memory left): V-side records — in the QK phase a lane IS its token, so right after the softmax weights it adds
+// p_g * delta to a per-warp fp32 accumulator [g][dim] in shared memory (red.shared.add.f32; dims of one token are distinct, lanes
+// collide rarely), rescaled with the warp's running max and folded into the warp's state at the end.  OUT = 0 is the plain
+// path, untouched.
+// P2P = 1: the group's last CTA also runs the cross-GPU exchange of the split-KV partitioning (merge_group<T, true>).
+template <typename T, int G, int VL, int OUT, int P2P>
 __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint32_t* __restrict__ prepared, const int gsub, const int split,
                                                   const int hk, const int sub, const int b, const int t0, const int t1, const int np, const int piece) {
     using namespace fast;
@@ -62,6 +67,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
     unsigned char* stage_p = smem + kStageOff;                           // kWarps * (K tile + V tile)
     unsigned char* pbuf_p = smem + kPbufOff;                             // kWarps * kTile * 8 bytes (4 halves per token)
     int* flag = reinterpret_cast<int*>(smem + kMiscOff);
+    float* vo_acc = reinterpret_cast<float*>(smem + kMiscOff + 1024) + (threadIdx.x >> 5) * (G * 128);   // OUT & 2: this warp's [g][dim]
     // after the main loop the stage buffers and p slots are dead: reuse them for the cross-warp combine and the merge
     float* xch = reinterpret_cast<float*>(stage_p);                      // 2 * kWarps * G * 130 floats, then kMergeScratch
 
@@ -167,6 +173,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         }
         issue(warp, kbase, ks_s);
         issue_v(warp);
+        pdl_wait();   // codes and tables are not written by the stream predecessor; q, the window and the workspace may be
         // K LUT: thread owns column `col` (= one sub-space) and walks the codes.  LUT[c][col] = <q_h[m], Kcent[m][c]> for the
         // G heads of the group: fp32 products of fp16 operands, rounded once to fp16 (G=1 keeps fp32 entries).  The gather table
         // kT (64 KB, L2 resident) is read straight into registers, 32 coalesced loads in flight per thread (staging it through
@@ -210,7 +217,10 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             }
         }
         cp_async_wait<2>();    // pending: [V table, K(0), V(0)] -> my part of the V table has landed
-        if constexpr (OUT) {
+        if constexpr ((OUT & 2) != 0) {
+            for (int i = lane; i < G * 128; i += 32) vo_acc[i] = 0.f;
+        }
+        if constexpr ((OUT & 1) != 0) {
             // q as a [dim][head] table for the outlier terms.  It takes the whole misc area (with G = 4 this kernel then uses
             // exactly 227 KB); the ticket flag and the merge mbarrier in there are only touched after the main loop.
             T* qt = reinterpret_cast<T*>(smem + kMiscOff);
@@ -218,6 +228,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 qt[i] = reinterpret_cast<const T*>(a.q)[(int64_t)(b * a.nh + h0 + (i % G)) * 128 + i / G];
         }
     }
+    if (!has_codes) pdl_wait();
     __syncthreads();
     dbg_stamp(a, 1, piece);
 
@@ -237,8 +248,18 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         // Raw load results only: nothing consumes them before the next iteration (a shift or an OR here would make this warp wait
         // for the HBM round trip on the spot).  k_out 1, 2, 4: one vector load each for dims and deltas; 3: byte-wise.
         uint32_t ko_dims = 0, ko_v01 = 0, ko_v23 = 0;
+        uint32_t vo_dims = 0, vo_v01 = 0, vo_v23 = 0;
+        auto vo_fetch = [&](int tile) {
+            if constexpr ((OUT & 2) != 0) {
+                const int tok = t0 + tile * kTile + lane;
+                const bool ok = tile < n_tiles && tok < t1;
+                const int64_t rec = hb * a.vo_head_stride + (int64_t)(ok ? tok : t0) * a.v_out;
+                ko_load(a.vo_idx + rec, reinterpret_cast<const unsigned short*>(a.vo_val) + rec, a.v_out, vo_dims, vo_v01, vo_v23);
+            }
+        };
+        vo_fetch(warp);
         auto ko_fetch = [&](int tile) {
-            if constexpr (OUT) {
+            if constexpr ((OUT & 1) != 0) {
                 const int tok = t0 + tile * kTile + lane;
                 const bool ok = tile < n_tiles && tok < t1;
                 const int64_t rec = hb * a.ko_head_stride + (int64_t)(ok ? tok : t0) * a.k_out;
@@ -255,6 +276,8 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             const bool valid = tok < t1;
             const uint32_t my_dims = ko_dims, my_v01 = ko_v01, my_v23 = ko_v23;
             ko_fetch(tile + kWarps);
+            const uint32_t my_vdims = vo_dims, my_vv01 = vo_v01, my_vv23 = vo_v23;
+            vo_fetch(tile + kWarps);
 
             // ------------------------------------------------ QK: 64 conflict-free LUT gathers for my token
             float s[G];
@@ -288,7 +311,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
 #pragma unroll
                     for (int w = 0; w < 16; ++w) qk_gathers(words[w], koff[w]);
             }
-            if constexpr (OUT) {
+            if constexpr ((OUT & 1) != 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (i < a.k_out) {
@@ -341,6 +364,11 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                         st.l[g] *= alpha;
 #pragma unroll
                         for (int sl = 0; sl < 4; ++sl) { st.o[sl][g][0] *= alpha; st.o[sl][g][1] *= alpha; }
+                        if constexpr ((OUT & 2) != 0) {      // warp-uniform branch: the V-outlier sums follow the same max
+                            __syncwarp();
+                            for (int i = lane; i < 128; i += 32) vo_acc[g * 128 + i] *= alpha;
+                            __syncwarp();
+                        }
                         st.m[g] = nm[g];
                     }
                 }
@@ -350,6 +378,19 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             for (int g = 0; g < G; ++g) {
                 p[g] = exp2_fast(s[g], st.m[g]);
                 st.l[g] += p[g];
+            }
+            if constexpr ((OUT & 2) != 0) {
+                // V-side outlier records of my token: o_g[dim] += p_g * delta (fp32, shared-memory reduction)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < a.v_out) {
+                        const uint32_t pair = i < 2 ? my_vv01 : my_vv23;
+                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : (pair & 0xffffu));
+                        const float dv = valid ? io<T>::to_f(*reinterpret_cast<const T*>(&hv)) : 0.f;
+                        const int dim = (my_vdims >> (8 * i)) & 0xff;
+#pragma unroll
+                        for (int g = 0; g < G; ++g) atomicAdd(vo_acc + g * 128 + dim, p[g] * dv);
+                    }
             }
             // p for the PV phase: 4 halves (8 bytes) per token
             // row-major V: slot = token with its two low bits swapped (tokens t and t+2 adjacent); transposed V: natural order
@@ -455,7 +496,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
         const int w0 = (int)((long long)rw * split / np), w1 = (int)((long long)rw * (split + 1) / np);
         // fused append: window row rw-1 is the token being decoded; it is read from k_new / v_new and stored into the window here
         // (by the one warp of the one split that owns that row), replacing the copy launch of pq_utils.py:304-311
-        const int t_new = a.k_new != nullptr ? rw - 1 : -1;
+        const int t_new = (a.k_new != nullptr && rw - 1 >= w0 && rw - 1 < w1) ? rw - 1 : -1;   // only the split that owns the row: the batched loads below also visit (masked) rows beyond w1
         if (w0 + warp < w1) {
             float qv[G][4];
 #pragma unroll
@@ -543,7 +584,11 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 for (int k = 0; k < 2; ++k) {
                     // partner (hw=1) slot (sl - 1) & 3 holds the same sub-space as my (hw=0) slot sl
                     const float theirs = __shfl_xor_sync(0xffffffffu, st.o[(sl + 3) & 3][g][k], 16);
-                    if (hw == 0) wx[g * 128 + 2 * (4 * lq + sl) + k] = st.o[sl][g][k] + theirs;
+                    if (hw == 0) {
+                        float v = st.o[sl][g][k] + theirs;
+                        if constexpr ((OUT & 2) != 0) { if (has_codes) v += vo_acc[g * 128 + 2 * (4 * lq + sl) + k]; }
+                        wx[g * 128 + 2 * (4 * lq + sl) + k] = v;
+                    }
                 }
         float* ww = xch + (kWarps + warp) * kEntry;
 #pragma unroll
@@ -587,20 +632,21 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
     // ---------------------------------------------------------------- last CTA of the (b, hk) group merges
     const bool last = last_cta_of_group(a.counters, hb, np * gsub, flag);
     dbg_stamp(a, 5, piece);
-    if (last) merge_group<T>(a, b, hk, np, xch, reinterpret_cast<float*>(lut_p), (LutCfg<G>::bytes + kVtabBytes) / 4,   // LUT + V table: both dead, adjacent
+    if (last) merge_group<T, P2P != 0>(a, b, hk, np, xch, reinterpret_cast<float*>(lut_p), (LutCfg<G>::bytes + kVtabBytes) / 4,   // LUT + V table: both dead, adjacent
                             
                              reinterpret_cast<unsigned long long*>(smem + kMiscOff + 160), piece);   // the K LUT is dead by now
     dbg_stamp(a, 6, piece);
 }
 
 // VL = 0: value codes row-major (tokens x 64 bytes); VL = 1: transposed per sub-space (paged pool or (M, ld) rows)
-template <typename T, int G, int VL, int OUT>
+template <typename T, int G, int VL, int OUT, int P2P>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
+    pdl_launch_dependents();   // a PDL successor may take the SMs this grid leaves; it waits for our completion before it reads q
     if (!a.flat) {
         // grid (splits, kv heads x 4-head sub-groups, batch): one segment per CTA
         int t0, t1;
         split_range(a, blockIdx.x, t0, t1);
-        attn_fast_segment<T, G, VL, OUT>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits, 0);
+        attn_fast_segment<T, G, VL, OUT, P2P>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits, 0);
         return;
     }
     // Flat scheduling: the (group, 64-token unit) space is cut into runs of equal COST, one per CTA, so every SM gets the
@@ -621,24 +667,24 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_kernel(const Attn
         const int first = (int)(real0 / per), last = (int)((real1 - 1) / per);
         const int us = (int)(s0 - real0), ue = (int)(s1 - real0);
         const int t1 = (ue * 64 < a.nk) ? ue * 64 : a.nk;
-        attn_fast_segment<T, G, VL, OUT>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1, piece++);
+        attn_fast_segment<T, G, VL, OUT, P2P>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1, piece++);
         __syncthreads();   // the next piece reuses every shared buffer
     }
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
-template <typename T, int G, int VL, int OUT>
+template <typename T, int G, int VL, int OUT, int P2P = 0>
 static int launch_fast_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
-    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + (OUT ? 1024 : 256);
+    static_assert((OUT & 2) == 0 || G <= 2, "V-side outlier accumulators need shared memory the G = 4 kernel does not have");
+    const size_t smem = LutCfg<G>::bytes + kVtabBytes + kWarps * kStageBytes + kWarps * kTile * 8 + (OUT ? 1024 : 256) + ((OUT & 2) ? kWarps * G * 128 * 4 : 0);
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= 2 * kWarps * 4 * 130 * sizeof(float), "stage + p area too small for the combine");
     static_assert(kWarps * kStageBytes + kWarps * kTile * 8 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static SmemAttrOnce configured = {};
-    MILLION_CUDA_OK(ensure_dynamic_smem(configured, attn_fast_kernel<T, G, VL, OUT>, smem));
+    MILLION_CUDA_OK(ensure_dynamic_smem(configured, attn_fast_kernel<T, G, VL, OUT, P2P>, smem));
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
     if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
-    attn_fast_kernel<T, G, VL, OUT><<<grid, block, smem, stream>>>(a, prepared, gsub);
-    MILLION_CUDA_OK(cudaGetLastError());
+    MILLION_CUDA_OK(launch_kernel(attn_fast_kernel<T, G, VL, OUT, P2P>, grid, block, smem, stream, a.pdl != 0, a, prepared, gsub));
     return MILLION_OK;
 }
 
@@ -649,7 +695,7 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     a.n_parts = a.n_splits;   // the window is dealt out to the splits, no extra part
     a.flat = 0;
     const int Gfull = a.nh / a.nh_k;
-    if (a.d != 128 || (a.M != 64 && a.M != 32) || a.C != 256) MILLION_UNSUPPORTED("fast decode attention needs d=128, M in {32, 64}, C=256");
+    if (a.d != 128 || (a.M != 64 && a.M != 32) || a.C != 256 || a.code_bytes != 1) MILLION_UNSUPPORTED("fast decode attention needs d=128, M in {32, 64}, C=256, one-byte codes");
     const bool dm4 = a.M == 32;
     if (dm4 && a.nk > 0 && a.v_layout != MILLION_V_ROWMAJOR) MILLION_UNSUPPORTED("fast decode attention, M=32: value codes must be row-major");
     if (!(Gfull == 1 || Gfull == 2 || Gfull % 4 == 0)) MILLION_UNSUPPORTED("fast decode attention needs nh/nh_k in {1,2,4k}");
@@ -657,11 +703,17 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
         MILLION_UNSUPPORTED("fast decode attention: paged V needs page_size %% 32 == 0 and an aligned pool");
     if (a.nk > 0 && a.v_layout == MILLION_V_TRANSPOSED && ((a.v_ld & 15) || (a.v_head_stride & 15) || ((uintptr_t)a.v_codes & 15)))
         MILLION_UNSUPPORTED("fast decode attention: transposed V needs 16-byte aligned rows");
-    if (a.nk > 0 && a.v_out > 0) MILLION_UNSUPPORTED("fast decode attention: V-side outlier records run on the generic kernel");
+    if (a.nk > 0 && a.v_out > 0 && (dm4 || Gfull > 2 || a.v_out > 4))
+        MILLION_UNSUPPORTED("fast decode attention: V-side outlier records need M=64, nh/nh_k <= 2 and v_out <= 4 (the generic kernel runs the rest)");
+    if (a.nk > 0 && a.v_out > 0 && a.v_out != 3 &&
+        ((uintptr_t)a.vo_idx % a.v_out || a.vo_head_stride % a.v_out || (uintptr_t)a.vo_val % (2 * a.v_out)))
+        MILLION_UNSUPPORTED("fast decode attention: the V-side outlier store must be aligned to one token's records");
     if (a.nk > 0 && a.k_out > 4) MILLION_UNSUPPORTED("fast decode attention: K-side outliers need k_out <= 4");
     if (a.nk > 0 && a.k_out > 0 && a.k_out != 3 &&
         ((uintptr_t)a.ko_idx % a.k_out || a.ko_head_stride % a.k_out || (uintptr_t)a.ko_val % (2 * a.k_out)))
         MILLION_UNSUPPORTED("fast decode attention: the K-side outlier store must be aligned to one token's records");
+    if (a.p2p && (Gfull != 4 || dm4 || a.v_layout != MILLION_V_ROWMAJOR || a.k_out || a.v_out))
+        MILLION_UNSUPPORTED("fused split-KV exchange: compiled for M=64, nh/nh_k = 4, row-major value codes, no side store (use MILLION_ATTN_PARTIAL_ONLY + million_splitkv_push_merge)");
     if (!prepared) MILLION_UNSUPPORTED("fast decode attention needs a prepared codebook (million_pq_codebook_prepare)");
     if (a.nk > 0 && (((uintptr_t)a.k_codes | (uintptr_t)a.k_head_stride) & 15))
         MILLION_UNSUPPORTED("fast decode attention needs 16-byte aligned code caches");
@@ -691,19 +743,30 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     }
     if (dm4) return launch_attn_fast_dm4(a, io_dtype, G, gsub, prepared, stream);
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
+    if (a.p2p) {   // checked above: G = 4 (one 4-head sub-group), row-major V, no side store
+        return io_dtype == MILLION_F16 ? launch_fast_t<__half, 4, 0, 0, 1>(a, prep, gsub, stream) : launch_fast_t<__nv_bfloat16, 4, 0, 0, 1>(a, prep, gsub, stream);
+    }
+    const int kv = (a.nk > 0 && a.k_out ? 1 : 0) | (a.nk > 0 && a.v_out ? 2 : 0);
 #define MILLION_FAST_CASE(TT, GG) \
-    return a.v_layout == MILLION_V_ROWMAJOR ? (a.k_out ? launch_fast_t<TT, GG, 0, 1>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 0, 0>(a, prep, gsub, stream)) \
-                                            : (a.k_out ? launch_fast_t<TT, GG, 1, 1>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1, 0>(a, prep, gsub, stream))
+    return a.v_layout == MILLION_V_ROWMAJOR ? (kv & 1 ? launch_fast_t<TT, GG, 0, 1>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 0, 0>(a, prep, gsub, stream)) \
+                                            : (kv & 1 ? launch_fast_t<TT, GG, 1, 1>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1, 0>(a, prep, gsub, stream))
+    // V-side records (alone or with K-side ones): G <= 2 only
+#define MILLION_FAST_CASE_V(TT, GG) \
+    return a.v_layout == MILLION_V_ROWMAJOR ? (kv == 3 ? launch_fast_t<TT, GG, 0, 3>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 0, 2>(a, prep, gsub, stream)) \
+                                            : (kv == 3 ? launch_fast_t<TT, GG, 1, 3>(a, prep, gsub, stream) : launch_fast_t<TT, GG, 1, 2>(a, prep, gsub, stream))
     if (io_dtype == MILLION_F16) {
+        if (kv & 2) { if (G == 2) MILLION_FAST_CASE_V(__half, 2); MILLION_FAST_CASE_V(__half, 1); }
         if (G == 4) MILLION_FAST_CASE(__half, 4);
         if (G == 2) MILLION_FAST_CASE(__half, 2);
         MILLION_FAST_CASE(__half, 1);
     } else {
+        if (kv & 2) { if (G == 2) MILLION_FAST_CASE_V(__nv_bfloat16, 2); MILLION_FAST_CASE_V(__nv_bfloat16, 1); }
         if (G == 4) MILLION_FAST_CASE(__nv_bfloat16, 4);
         if (G == 2) MILLION_FAST_CASE(__nv_bfloat16, 2);
         MILLION_FAST_CASE(__nv_bfloat16, 1);
     }
 #undef MILLION_FAST_CASE
+#undef MILLION_FAST_CASE_V
 }
 
 }  // namespace million

@@ -347,7 +347,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
     {
         const int rw = window_rows(a);
         const int w0 = (int)((long long)rw * split / np), w1 = (int)((long long)rw * (split + 1) / np);
-        const int t_new = a.k_new != nullptr ? rw - 1 : -1;   // fused window append, as in attn_fast.cu
+        const int t_new = (a.k_new != nullptr && rw - 1 >= w0 && rw - 1 < w1) ? rw - 1 : -1;   // only the split that owns the row: the batched loads below also visit (masked) rows beyond w1   // fused window append, as in attn_fast.cu
         if (w0 + warp < w1) {
             float qv[G][4];
 #pragma unroll
@@ -450,6 +450,8 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
 
 template <typename T, int G, int OUT>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_dm4_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
+    pdl_launch_dependents();
+    pdl_wait();            // PDL here only hides the launch latency (attn_fast.cu also overlaps its table copies and first tiles)
     if (!a.flat) {
         int t0, t1;
         split_range(a, blockIdx.x, t0, t1);
@@ -483,8 +485,7 @@ static int launch_dm4_t(const AttnArgs& a, const uint32_t* prepared, int gsub, c
     MILLION_CUDA_OK(ensure_dynamic_smem(configured, attn_fast_dm4_kernel<T, G, OUT>, smem));
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
     if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
-    attn_fast_dm4_kernel<T, G, OUT><<<grid, block, smem, stream>>>(a, prepared, gsub);
-    MILLION_CUDA_OK(cudaGetLastError());
+    MILLION_CUDA_OK(launch_kernel(attn_fast_dm4_kernel<T, G, OUT>, grid, block, smem, stream, a.pdl != 0, a, prepared, gsub));
     return MILLION_OK;
 }
 

@@ -11,9 +11,11 @@ namespace million {
 
 template <typename T>
 __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* lut = reinterpret_cast<float*>(smem_raw);  // M*C (coded splits) or d (window: q)
-    float* qs = lut + a.M * a.C;                      // coded splits with K outliers: q * scale, d floats
+    float* lut = reinterpret_cast<float*>(smem_raw);  // M*C (coded splits) or d (window: q); not used in direct mode
+    float* qs = lut + (a.direct ? 0 : a.M * a.C);     // coded splits with K outliers / direct mode: q * scale, d floats
     __shared__ float P[128];
     __shared__ float red[33];
     __shared__ float mscr[kMergeScratch];
@@ -37,14 +39,15 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
         if (window) {
             for (int i = tid; i < a.d; i += 128) lut[i] = io<T>::to_f(q[i]) * a.scale_log2;
         } else if (t1 > t0) {
-            for (int i = tid; i < a.M * a.C; i += 128) {
-                const int m = i / a.C;
-                float acc = 0.f;
-                for (int k = 0; k < dm; ++k)
-                    acc = fmaf(io<T>::to_f(q[m * dm + k]), io<T>::to_f(kcent[(int64_t)i * dm + k]), acc);
-                lut[i] = acc * a.scale_log2;
-            }
-            if (a.k_out)
+            if (!a.direct)
+                for (int i = tid; i < a.M * a.C; i += 128) {
+                    const int m = i / a.C;
+                    float acc = 0.f;
+                    for (int k = 0; k < dm; ++k)
+                        acc = fmaf(io<T>::to_f(q[m * dm + k]), io<T>::to_f(kcent[(int64_t)i * dm + k]), acc);
+                    lut[i] = acc * a.scale_log2;
+                }
+            if (a.k_out || a.direct)
                 for (int i = tid; i < a.d; i += 128) qs[i] = io<T>::to_f(q[i]) * a.scale_log2;
         }
         __syncthreads();
@@ -61,9 +64,18 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const AttnArgs a) {
                     for (int k = 0; k < a.d; ++k) acc_s = fmaf(lut[k], io<T>::to_f(kr[k]), acc_s);
                     s = acc_s;
                 } else {
-                    const uint8_t* kc = a.k_codes + hb * a.k_head_stride + (int64_t)j * a.M;
                     float acc_s = 0.f;
-                    for (int m = 0; m < a.M; ++m) acc_s += lut[m * a.C + kc[m]];
+                    if (!a.direct) {
+                        for (int m = 0; m < a.M; ++m) acc_s += lut[m * a.C + k_code_at(a, hb, j, m)];
+                    } else {
+                        // large codebooks (nbits > 8): the same sum, sub-space by sub-space, straight from the centroids (L2 resident)
+                        for (int m = 0; m < a.M; ++m) {
+                            const T* c = kcent + ((int64_t)m * a.C + k_code_at(a, hb, j, m)) * dm;
+                            float part = 0.f;
+                            for (int k = 0; k < dm; ++k) part = fmaf(qs[m * dm + k], io<T>::to_f(c[k]), part);
+                            acc_s += part;
+                        }
+                    }
                     if (a.k_out) {   // outlier side store: x_hat[dim] = centroid + delta
                         const int64_t rec = hb * a.ko_head_stride + (int64_t)j * a.k_out;
                         for (int i = 0; i < a.k_out; ++i)
@@ -121,14 +133,15 @@ int launch_attn_generic(const AttnArgs& a_in, int io_dtype, cudaStream_t stream)
     AttnArgs a = a_in;
     a.n_parts = a.n_splits + 1;
     if (a.d > 256) MILLION_UNSUPPORTED("generic decode attention supports d <= 256 (got %d)", a.d);
-    const size_t smem = sizeof(float) * (size_t)(a.M * a.C + a.d);
+    a.direct = (size_t)a.M * a.C * sizeof(float) > 160 * 1024;       // e.g. M=64, C=1024 (nbits 10): 256 KB of LUT do not fit
+    const size_t smem = sizeof(float) * ((a.direct ? 0 : (size_t)a.M * a.C) + a.d);
     dim3 grid(a.n_splits + 1, a.nh_k, a.bs), block(128);
     if (io_dtype == MILLION_F16) {
         MILLION_CUDA_OK(cudaFuncSetAttribute(attn_generic_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_generic_kernel<__half><<<grid, block, smem, stream>>>(a);
+        MILLION_CUDA_OK(launch_kernel(attn_generic_kernel<__half>, grid, block, smem, stream, a.pdl != 0, a));
     } else {
         MILLION_CUDA_OK(cudaFuncSetAttribute(attn_generic_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_generic_kernel<__nv_bfloat16><<<grid, block, smem, stream>>>(a);
+        MILLION_CUDA_OK(launch_kernel(attn_generic_kernel<__nv_bfloat16>, grid, block, smem, stream, a.pdl != 0, a));
     }
     MILLION_CUDA_OK(cudaGetLastError());
     return MILLION_OK;

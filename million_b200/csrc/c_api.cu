@@ -239,16 +239,16 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
                     p->struct_size, sizeof(million_attn_params));
     MILLION_REQUIRE(p->io_dtype == MILLION_F16 || p->io_dtype == MILLION_BF16, "attn: io_dtype must be f16 or bf16");
     MILLION_REQUIRE(p->bs >= 0 && p->nh > 0 && p->nh_k > 0 && p->nh % p->nh_k == 0, "attn: bad head counts");
-    MILLION_REQUIRE(p->M > 0 && p->d % p->M == 0 && p->C > 1 && p->C <= 256, "attn: bad d/M/C (%d/%d/%d)", p->d, p->M, p->C);
+    const int code_bytes = p->code_bytes == 0 ? 1 : p->code_bytes;
+    MILLION_REQUIRE(code_bytes == 1 || code_bytes == 2, "attn: code_bytes must be 1 (uint8) or 2 (uint16)");
+    MILLION_REQUIRE(p->M > 0 && p->d % p->M == 0 && p->C > 1 && p->C <= (code_bytes == 1 ? 256 : 65536), "attn: bad d/M/C (%d/%d/%d) for %d-byte codes", p->d, p->M, p->C, code_bytes);
     MILLION_REQUIRE(p->nk >= 0 && p->r >= 0 && p->r <= p->res_len, "attn: bad nk/r (nk=%d r=%d res_len=%d)", p->nk, p->r, p->res_len);
     if (p->bs == 0) return MILLION_OK;
     const bool partial_only = (p->flags & MILLION_ATTN_PARTIAL_ONLY) != 0;
     const bool fused_splitkv = (p->flags & MILLION_ATTN_FUSED_SPLITKV) != 0;
     MILLION_REQUIRE(!(partial_only && fused_splitkv), "attn: PARTIAL_ONLY and FUSED_SPLITKV exclude each other");
-#ifndef MILLION_FUSED_SPLITKV
-    if (fused_splitkv) MILLION_UNSUPPORTED("attn: this build has no fused split-KV exchange (experimental: rebuild with -DMILLION_FUSED_SPLITKV); use MILLION_ATTN_PARTIAL_ONLY + million_splitkv_push_merge");
-#endif
-    if (fused_splitkv) MILLION_REQUIRE((int64_t)p->bs * p->nh <= 256, "attn: fused split-KV serves at most 256 (batch, head) rows");
+    if (fused_splitkv) MILLION_REQUIRE((int64_t)p->bs * p->nh_k <= kP2PMaxGroups, "attn: fused split-KV serves at most %d (batch, kv-head) groups", kP2PMaxGroups);
+    if (fused_splitkv) MILLION_REQUIRE(p->out != nullptr, "attn: fused split-KV writes the merged result to `out`");
     if (fused_splitkv) MILLION_REQUIRE(p->p2p_state != nullptr && ((uintptr_t)p->p2p_state & 15) == 0, "attn: fused split-KV needs the (16-byte aligned) state block of million_splitkv_state_init");
     MILLION_REQUIRE(p->q && p->k_cent && p->v_cent && p->workspace, "attn: null pointer");
     MILLION_REQUIRE(partial_only ? (p->partial != nullptr) : (p->out != nullptr), "attn: missing output pointer");
@@ -262,7 +262,7 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
         MILLION_REQUIRE(p->v_page_ids && p->page_size > 0, "attn: paged V needs page ids and page_size");
         MILLION_REQUIRE((int64_t)p->n_pages * p->page_size >= p->nk, "attn: %d pages of %d < nk=%d", p->n_pages, p->page_size, p->nk);
     }
-    if (p->nk > 0) MILLION_REQUIRE(p->k_head_stride >= (int64_t)p->nk * p->M, "attn: k_head_stride too small");
+    if (p->nk > 0) MILLION_REQUIRE(p->k_head_stride >= (int64_t)p->nk * p->M * code_bytes, "attn: k_head_stride too small");
 
     int S = p->n_splits > 0 ? p->n_splits : million_pq_decode_attn_default_splits(p->bs, p->nh_k, p->nk);
     MILLION_REQUIRE(p->workspace_bytes >= million_pq_decode_attn_workspace_bytes(p->bs, p->nh, p->nh_k, p->d, S),
@@ -287,7 +287,8 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     if (a.units_per_split < 4) a.units_per_split = 4;
     MILLION_REQUIRE(S + 1 <= 1024, "attn: at most 1023 splits");
     a.scale_log2 = kLog2e / sqrtf((float)p->d);
-    if (fused_splitkv) a.partial_out = reinterpret_cast<float*>(reinterpret_cast<uintptr_t>(p->p2p_state) | 1);   // tagged: see AttnArgs
+    if (fused_splitkv) { a.partial_out = reinterpret_cast<float*>(p->p2p_state); a.p2p = 1; }
+    a.pdl = (p->flags & MILLION_ATTN_PDL) != 0;
     if (p->nk > 0 && p->k_out > 0 && p->k_out_idx && p->k_out_val) {
         MILLION_REQUIRE(p->k_out <= MILLION_MAX_OUTLIERS && p->d <= 256, "attn: k_out %d > %d or d > 256", p->k_out, MILLION_MAX_OUTLIERS);
         MILLION_REQUIRE(p->k_out_head_stride >= (int64_t)p->nk * p->k_out, "attn: k_out_head_stride too small");
@@ -299,6 +300,7 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
         a.v_out = p->v_out; a.vo_idx = p->v_out_idx; a.vo_val = p->v_out_val; a.vo_head_stride = p->v_out_head_stride;
     }
     a.k_new = p->k_new; a.v_new = p->v_new; a.r_dev = p->r_dev;
+    a.code_bytes = code_bytes;
 #ifdef MILLION_DEBUG
     a.dbg_timing = g_dbg_timing;
     a.dbg_mode = g_dbg_mode;
@@ -308,6 +310,7 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     const bool fast_ok = p->impl != MILLION_IMPL_GENERIC &&
                          (p->impl == MILLION_IMPL_FAST || launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, true) == MILLION_OK);
     if (fast_ok) return launch_attn_fast(a, p->io_dtype, p->prepared_codebook, st, false);   // appends the new token itself
+    if (fused_splitkv) MILLION_UNSUPPORTED("attn: the fused split-KV exchange exists in the fast kernel only (M=64, nh/nh_k = 4, row-major V)");
     if (a.k_new) {
         // the all-shapes kernel reads the window only: append with a copy launch first (same device-resident row index)
         int rc = launch_window_append_dev(const_cast<void*>(p->k_res), const_cast<void*>(p->v_res), (int64_t)p->res_len * p->d * 2, p->k_new, p->v_new,

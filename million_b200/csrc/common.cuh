@@ -58,6 +58,25 @@ inline cudaError_t ensure_dynamic_smem(SmemAttrOnce& st, F func, size_t bytes) {
     return e;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: the next kernel of the stream (if launched with the programmatic-serialization attribute) may start its
+// prologue on SMs this grid no longer occupies.  wait: returns once the previous grid has completed and its writes are visible
+// (immediately when the launch carried no such dependency).  Everything a kernel reads BEFORE its wait must not be produced by
+// its stream predecessor.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------- dtype traits
 template <typename T> struct io;
 template <> struct io<__half> {

@@ -273,7 +273,7 @@ def prepare_codebooks(k_cent, v_cent):
 
 def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=None, v_layout=L.V_ROWMAJOR,
                    v_page_ids=None, page_size=0, out=None, partial=None, n_splits=0, impl=L.IMPL_AUTO, workspace=None,
-                   prepared=None, k_outliers=None, v_outliers=None, p2p=None, k_new=None, v_new=None, r_dev=None):
+                   prepared=None, k_outliers=None, v_outliers=None, p2p=None, k_new=None, v_new=None, r_dev=None, pdl=False):
     """One decode-attention call (include/million_b200.h: million_pq_decode_attn).
 
     q (bs, nh, 1, d) | (bs, nh, d); k_codes (bs, nh_k, >=nk, M) uint8 (head stride taken from the tensor);
@@ -297,6 +297,8 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
     p = L.AttnParams()
     p.struct_size = ctypes.sizeof(L.AttnParams)
     p.io_dtype, p.impl, p.flags = _dt(q), impl, (L.ATTN_PARTIAL_ONLY if partial is not None else 0)
+    if pdl:
+        p.flags |= L.ATTN_PDL       # programmatic dependent launch: see MILLION_ATTN_PDL in include/million_b200.h
     if p2p is not None:
         assert partial is None
         p.flags |= L.ATTN_FUSED_SPLITKV
@@ -304,16 +306,20 @@ def pq_decode_attn(q, k_codes, v_codes, k_cent, v_cent, k_res, v_res, r, *, nk=N
     p.bs, p.nh, p.nh_k, p.d, p.M, p.C, p.nk, p.r = bs, nh, nh_k, d, M, C, nk, r
     p.q = q.data_ptr()
     if nk:
-        assert k_codes.dtype == torch.uint8 and k_codes.stride(3) == 1 and k_codes.stride(2) == M
+        # one-byte codes (uint8) or two-byte codes (uint16 / int16 storage: nbits2dtype for nbits > 8); ABI strides are in bytes
+        es = k_codes.element_size()
+        assert k_codes.dtype in (torch.uint8, torch.uint16, torch.int16) and v_codes.dtype == k_codes.dtype
+        assert k_codes.stride(3) == 1 and k_codes.stride(2) == M
         assert bs == 1 or k_codes.stride(0) == nh_k * k_codes.stride(1)
-        p.k_codes, p.k_head_stride = k_codes.data_ptr(), (k_codes.stride(1) if nh_k > 1 or bs > 1 else k_codes.shape[2] * M)
+        p.code_bytes = es
+        p.k_codes, p.k_head_stride = k_codes.data_ptr(), es * (k_codes.stride(1) if nh_k > 1 or bs > 1 else k_codes.shape[2] * M)
         p.v_codes = v_codes.data_ptr()
         if v_layout == L.V_ROWMAJOR:
             assert v_codes.stride(3) == 1 and v_codes.stride(2) == M
-            p.v_head_stride = v_codes.stride(1) if nh_k > 1 or bs > 1 else v_codes.shape[2] * M
+            p.v_head_stride = es * (v_codes.stride(1) if nh_k > 1 or bs > 1 else v_codes.shape[2] * M)
         elif v_layout == L.V_TRANSPOSED:
             assert v_codes.stride(3) == 1
-            p.v_head_stride, p.v_ld = v_codes.stride(1), v_codes.stride(2)
+            p.v_head_stride, p.v_ld = es * v_codes.stride(1), es * v_codes.stride(2)
         else:
             assert v_codes.is_contiguous() and v_page_ids.dtype == torch.int64 and v_page_ids.is_contiguous()
             p.v_page_ids, p.n_pages, p.page_size = v_page_ids.data_ptr(), v_page_ids.shape[2], page_size or v_codes.shape[2]

@@ -489,8 +489,10 @@ class DynamicPQCache(metaclass=Singleton):
         """The reference's route: KernelRegistry -> named binding (pq_utils.py:313-327); side stores go through ops directly."""
         kc, vc = self._attn_cents(query_states.dtype)
         ks = self._k[layer_idx]
-        if self.k_out or self.v_out:
-            # the reference's 10-argument kernel signature (pq_utils.py:83-94) has no place for the side store
+        if self.k_out or self.v_out or self.nbits != 8:
+            # the reference's 10-argument kernel signature (pq_utils.py:83-94) has no place for the side store, and its registry
+            # refuses nbits != 8 ("Only uint8 code type is supported for now", pq_utils.py:58-59): two-byte codes go straight
+            # to the C ABI (code_bytes = 2, all-shapes kernel)
             return ops.pq_decode_attn(query_states, ks.view(), self._v[layer_idx].view(), kc, vc,
                                       self.key_residual_cache[layer_idx], self.value_residual_cache[layer_idx],
                                       self.residualed_tokens[layer_idx],
@@ -506,7 +508,7 @@ class DynamicPQCache(metaclass=Singleton):
 
     def _fill_v(self, p, layer_idx):
         vs = self._v[layer_idx]
-        p.v_layout, p.v_codes, p.v_head_stride = L.V_ROWMAJOR, vs.buf.data_ptr(), vs.cap * self.M
+        p.v_layout, p.v_codes, p.v_head_stride = L.V_ROWMAJOR, vs.buf.data_ptr(), vs.cap * self.M * vs.buf.element_size()
 
     def _plan(self, layer_idx, dtype, device):
         """Per-layer, pre-filled million_attn_params (the per-call Python work is what bounds batch-1 decode).  Dropped by
@@ -519,7 +521,9 @@ class DynamicPQCache(metaclass=Singleton):
             p = L.AttnParams()
             p.struct_size = ctypes.sizeof(L.AttnParams)
             p.io_dtype = ops._DT[dtype]
-            p.impl, p.flags = L.IMPL_AUTO, 0
+            # PDL: the launch may begin (table copies, first code tiles) while its stream predecessor drains; nothing the
+            # predecessor can write — q, k/v of the new token, window, workspace — is read before it has completed
+            p.impl, p.flags = L.IMPL_AUTO, L.ATTN_PDL
             p.bs, p.nh, p.nh_k, p.d, p.M, p.C = self.bs, self.nh, self.num_key_value_heads, self.d, self.M, kc.shape[1]
             p.v_layout = L.V_ROWMAJOR
             p.k_cent, p.v_cent = kc.data_ptr(), vc.data_ptr()
@@ -540,7 +544,7 @@ class DynamicPQCache(metaclass=Singleton):
         ks = self._k[layer_idx]
         p.nk = ks.len
         if ks.len:
-            p.k_codes, p.k_head_stride = ks.buf.data_ptr(), ks.cap * self.M
+            p.k_codes, p.k_head_stride = ks.buf.data_ptr(), ks.cap * self.M * ks.buf.element_size()
             self._fill_v(p, layer_idx)
             if self.k_out:
                 ko = self._ko[layer_idx]

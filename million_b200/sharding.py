@@ -85,7 +85,7 @@ class SplitKVPeerGroup:
         torch.cuda.synchronize()
         dist.barrier(self.group)
 
-    def merge(self, out=None):
+    def merge(self, out=None, pdl=False):
         """Push self.partial to every rank and merge everybody's state; returns (rows, d)."""
         import ctypes
         from . import _lib as L
@@ -95,21 +95,36 @@ class SplitKVPeerGroup:
         st = ctypes.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)
         L.check(L.lib().million_splitkv_push_merge(ctypes.c_void_p(self.partial.data_ptr()), ctypes.cast(self._peer_array, ctypes.c_void_p),
                                                    self.rank, self.world, self.rows, self.d, ctypes.c_void_p(out.data_ptr()), _DT[self.dtype],
-                                                   ctypes.c_void_p(self.state.data_ptr()), st))
+                                                   ctypes.c_void_p(self.state.data_ptr()), L.ATTN_PDL if pdl else 0, st))
         return out
 
-    def decode_attn(self, q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, out=None, fused=False, **attn_kw):
-        """fused=True: ONE launch per layer — the attention kernel's own merge epilogue pushes this rank's state to the peers,
-        waits for theirs and writes the merged result (MILLION_ATTN_FUSED_SPLITKV); otherwise attention + million_splitkv_push_merge."""
+    def decode_attn(self, q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, out=None, fused=False, pdl=False, **attn_kw):
+        """fused=True: ONE launch per layer — the last CTA of every (b, kv-head) group pushes the group's rows to the peers, waits
+        for theirs and writes the merged rows (MILLION_ATTN_FUSED_SPLITKV; M=64, nh/nh_k = 4, row-major V); otherwise attention +
+        million_splitkv_push_merge.  pdl=True launches with programmatic dependent launch (MILLION_ATTN_PDL)."""
         from . import ops
         bs, nh, d = q.shape[0], q.shape[1], q.shape[-1]
         if fused:
             assert bs * nh == self.rows
             return ops.pq_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, out=out,
-                                      p2p=self.state, **attn_kw)
-        ops.pq_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, partial=self.partial, **attn_kw)
-        o = self.merge(None if out is None else out.view(bs * nh, d))
+                                      p2p=self.state, pdl=pdl, **attn_kw)
+        ops.pq_decode_attn(q, k_codes_local, v_codes_local, k_cent, v_cent, k_res, v_res, r_local, partial=self.partial, pdl=pdl, **attn_kw)
+        o = self.merge(None if out is None else out.view(bs * nh, d), pdl=pdl)
         return o.view(bs, nh, 1, d)
+
+    def set_timeout(self, microseconds):
+        """How long a wait for the peers may last before the kernel gives up (NaN rows + error word); 0 = the default (~0.8 s)."""
+        import ctypes
+        from . import _lib as L
+        L.check(L.lib().million_splitkv_set_timeout(ctypes.c_void_p(self.state.data_ptr()), int(microseconds),
+                                                    ctypes.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)))
 
     def timed_out(self):
         return bool(self.state.view(torch.int32)[2].item())
+
+    def check(self):
+        """Raise if any exchange since the last check gave up waiting for a peer (synchronises the device: call it at a
+        convenient point — e.g. once per generated token — not per layer).  The affected output rows are NaN as well."""
+        if self.timed_out():
+            self.state.view(torch.int32)[2] = 0
+            raise RuntimeError(f"split-KV exchange on rank {self.rank}: a peer did not publish its state in time (dead or stalled rank)")

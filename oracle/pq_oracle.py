@@ -534,6 +534,7 @@ def make_inputs(*, bs, nh, nh_k, nk, d=128, M=64, C=256, Lt=128, seed=42, self_c
         K, V = f(bs, nh_k, nk, d), f(bs, nh_k, nk, d)
         kc, vc = pq_encode(K, kcent), pq_encode(V, vcent)
     else:
-        kc = rng.integers(0, C, (bs, nh_k, nk, M), dtype=np.uint8)
-        vc = rng.integers(0, C, (bs, nh_k, nk, M), dtype=np.uint8)
+        ct = np.uint8 if C <= 256 else np.uint16              # nbits2dtype
+        kc = rng.integers(0, C, (bs, nh_k, nk, M), dtype=ct)
+        vc = rng.integers(0, C, (bs, nh_k, nk, M), dtype=ct)
     return dict(q=q, kc=kc, vc=vc, kcent=kcent, vcent=vcent, kres=kres, vres=vres)

@@ -292,31 +292,73 @@ def test_partial_and_lse_merge_equals_single_call(M):
     np.testing.assert_allclose(merged.float().cpu().numpy(), full.float().cpu().numpy(), atol=1e-3, rtol=5e-3)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
-@pytest.mark.parametrize("bs,nh,nh_k,nk", [(1, 8, 2, 3000), (2, 4, 4, 700), (8, 8, 2, 4100)])
-def test_fused_splitkv_world1_equals_plain_call(M, impl, bs, nh, nh_k, nk):
-    """MILLION_ATTN_FUSED_SPLITKV with a world of one rank (the protocol degenerates to push-to-self, flag, merge of one part): same
-    result as the plain call, on consecutive launches (sequence parity flips), no timeout.  The multi-rank run is
-    tools/splitkv_nccl.py --p2p --fused."""
-    import ctypes
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bs,nh,nh_k,nk", [(1, 32, 8, 33000), (1, 8, 2, 3000), (8, 8, 2, 4100), (3, 16, 4, 0)])
+def test_fused_splitkv_world1_equals_plain_call(M, dtype, bs, nh, nh_k, nk):
+    """MILLION_ATTN_FUSED_SPLITKV with a world of one rank (the protocol degenerates to push-to-self, per-group flag, merge of one
+    part): same result as the plain call, on consecutive launches (sequence parity flips), no timeout, with and without PDL.
+    The multi-rank run is bench.py --gpus N (extra.splitkv_128k) and tools/splitkv_nccl.py --p2p --fused."""
     from million_b200 import _lib as L
     inp = O.make_inputs(bs=bs, nh=nh, nh_k=nh_k, nk=nk, seed=5)
     t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    for k in ("q", "kcent", "vcent", "kres", "vres"):
+        t[k] = t[k].to(dtype)
     rows, d = bs * nh, 128
     buf = torch.zeros(L.lib().million_splitkv_symmetric_bytes(1, rows, d), dtype=torch.uint8, device="cuda")
     state = M.splitkv_state([buf.data_ptr()], 0, rows, buf.device)
+    n = 0
     for r in (128, 17, 1):
-        plain = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl)
-        try:
-            fused = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=impl,
-                                     p2p=state)
-        except L.MillionError as e:
-            if e.status == L.MILLION_ERR_UNSUPPORTED:
-                pytest.skip("library built without -DMILLION_FUSED_SPLITKV (the default: the option is experimental)")
-            raise
-        np.testing.assert_allclose(fused.float().cpu().numpy(), plain.float().cpu().numpy(), atol=2e-3, rtol=1e-2)
+        for pdl in (False, True):
+            plain = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r)
+            fused = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, p2p=state, pdl=pdl)
+            n += 1
+            np.testing.assert_allclose(fused.float().cpu().numpy(), plain.float().cpu().numpy(), atol=2e-3, rtol=1e-2)
     st = state.view(torch.int32).cpu().numpy()
-    assert st[0] == 3 and st[1] == 0 and st[2] == 0          # three completed calls, ticket back to zero, no timeout
+    assert st[0] == n and st[1] == 0 and st[2] == 0          # n completed calls, ticket back to zero, no timeout
+
+
+def test_fused_splitkv_unsupported_shapes_say_so(M):
+    from million_b200 import _lib as L
+    inp = O.make_inputs(bs=1, nh=8, nh_k=8, nk=500, seed=5)           # MHA: the fused exchange is compiled for nh/nh_k = 4
+    t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    buf = torch.zeros(L.lib().million_splitkv_symmetric_bytes(1, 8, 128), dtype=torch.uint8, device="cuda")
+    state = M.splitkv_state([buf.data_ptr()], 0, 8, buf.device)
+    with pytest.raises(L.MillionError) as e:
+        M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 5, p2p=state)
+    assert e.value.status == L.MILLION_ERR_UNSUPPORTED
+
+
+def test_pdl_launches_match_plain_launches(M):
+    """MILLION_ATTN_PDL: back-to-back launches that overlap their prologue with the predecessor's tail give bit-identical results
+    (fast M=64, fast M=32 and generic kernels), also inside a CUDA graph."""
+    for Mm, impl in ((64, 0), (32, 0), (64, 1)):
+        inp = O.make_inputs(bs=2, nh=32, nh_k=8, nk=3000, M=Mm, seed=8)
+        t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+        outs = [torch.empty(2, 32, 1, 128, dtype=torch.float16, device="cuda") for _ in range(6)]
+        want = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 77, impl=impl).clone()
+
+        def run():
+            for o in outs:
+                M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 77, impl=impl, out=o, pdl=True)
+        run()
+        torch.cuda.synchronize()
+        for o in outs:
+            assert torch.equal(o, want)
+            o.zero_()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            run()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run()
+        for o in outs:
+            o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for o in outs:
+            assert torch.equal(o, want)
 
 
 def test_full_size_llama31_8b_32k_properties(M):

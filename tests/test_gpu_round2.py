@@ -415,3 +415,67 @@ def test_debug_hooks_are_not_in_the_product_build():
     from million_b200 import _lib as L
     with pytest.raises(AttributeError):     # ctypes resolves symbols on attribute access
         getattr(L.lib(), "million_debug_set_mode")
+
+
+# ------------------------------------------------------------------------------------------------ nbits > 8 (uint16 codes)
+
+
+@pytest.mark.parametrize("Mm,C", [(64, 512), (64, 1024), (32, 4096)])
+@pytest.mark.parametrize("v_layout", [0, 1, 2])
+def test_attn_two_byte_codes(M, Mm, C, v_layout):
+    """nbits in 9..12 (results.jsonl:3-5,18-20): uint16 codes (nbits2dtype, pq_utils.py:542-552), codebooks of 512..4096 centroids.
+    The reference compiles no kernel for them (pq_utils.py:58-59); ours runs them on the all-shapes kernel (LUT in shared memory
+    while it fits, scores straight from the centroids beyond).  Against the oracle, every value layout."""
+    from million_b200 import _lib as L
+    bs, nh, nh_k, nk, r, d = 2, 8, 4, 700, 33, 128
+    inp = O.make_inputs(bs=bs, nh=nh, nh_k=nh_k, nk=nk, d=d, M=Mm, C=C, Lt=128, seed=Mm + C)
+    assert inp["kc"].dtype == np.uint16 and inp["kc"].max() > 255
+    t = {k: dev(v.view(np.int16) if v.dtype == np.uint16 else v) for k, v in inp.items()}
+    kw = {}
+    if v_layout == 0:
+        vc = t["vc"]
+    elif v_layout == 1:
+        vc = t["vc"].transpose(2, 3).contiguous()
+    else:
+        pool, table = O.build_page_pool(inp["vc"], 64)
+        vc, kw = dev(pool.view(np.int16)), dict(v_page_ids=dev(table), page_size=64)
+    out = M.pq_decode_attn(t["q"], t["kc"], vc, t["kcent"], t["vcent"], t["kres"], t["vres"], r, nk=nk, v_layout=v_layout, **kw)
+    ref = O.pq_decode_attn(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], r)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=ATOL, rtol=RTOL)
+    with pytest.raises(L.MillionError):      # the fast kernels are one-byte only and say so
+        M.pq_decode_attn(t["q"], t["kc"], vc, t["kcent"], t["vcent"], t["kres"], t["vres"], r, nk=nk, v_layout=v_layout, impl=L.IMPL_FAST, **kw)
+
+
+def test_encode_decode_two_byte_codes(M):
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    X = torch.randn(2, 4, 300, 128, device="cuda", generator=g).half()
+    cent = torch.randn(64, 1024, 2, device="cuda", generator=g).half().float().contiguous()
+    codes = M.pq_encode(X, cent, out_dtype=torch.uint16)
+    assert codes.dtype == torch.uint16
+    want = O.pq_encode(X.float().cpu().numpy(), cent.cpu().numpy(), out_dtype=np.uint16)
+    assert np.array_equal(codes.cpu().numpy(), want)
+    rec = M.pq_decode(codes, cent.half())
+    assert np.array_equal(rec.float().cpu().numpy(), O.pq_decode(want, cent.half().float().cpu().numpy()))
+
+
+def test_dynamic_cache_nbits10_follows_the_oracle():
+    """DynamicPQCache(dtype=nbits2dtype(10), nbits=10) as main_pq.py:134,337-347 builds it: prefill, decode across a flush."""
+    from million_b200.pq_utils import DynamicPQCache, nbits2dtype
+    kw = dict(bs=1, nh=8, num_key_value_heads=2, M=64, layer_num=1, d=128, nbits=10)
+    rng = np.random.default_rng(4)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32).astype(np.float16)
+    kc, vc = f(64, 1024, 2), f(64, 1024, 2)
+    cache = _mk(DynamicPQCache, scalar_t=torch.float16, dtype=nbits2dtype(10), **kw)
+    cache.set_cent(dev(kc), dev(vc))
+    oracle = O.DynamicPQCacheOracle(**kw)
+    oracle.set_cent(kc, vc)
+    q, k, v = f(1, 8, 50, 128), f(1, 2, 50, 128), f(1, 2, 50, 128)
+    out = cache.prefill(dev(q), dev(k), dev(v), 0)
+    np.testing.assert_allclose(out.float().cpu().numpy(), oracle.prefill(q, k, v, 0), atol=ATOL, rtol=RTOL)
+    for step in range(135):
+        q, k, v = f(1, 8, 1, 128), f(1, 2, 1, 128), f(1, 2, 1, 128)
+        out = cache.decoding(dev(q), dev(k), dev(v), 0)
+        np.testing.assert_allclose(out.float().cpu().numpy(), oracle.decoding(q, k, v, 0), atol=ATOL, rtol=RTOL, err_msg=f"step {step}")
+    assert cache.key_cache[0].dtype == torch.uint16 and cache.key_cache[0].shape == (1, 2, 50 + 128, 64)
+    assert np.array_equal(cache.key_cache[0].cpu().numpy(), oracle.key_cache[0])
+    assert np.array_equal(cache.value_cache[0].cpu().numpy(), oracle.value_cache[0])

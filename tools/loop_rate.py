@@ -1,7 +1,7 @@
 """Main-loop cost of the decode kernel in clk per coded token and SM: slope of the launch time between two context lengths
 (fixed per-CTA costs cancel).  python tools/loop_rate.py [bs] [mode ...]"""
 import ctypes, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("MILLION_PKG_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # MILLION_PKG_ROOT: A/B against another tree (e.g. variants/r1)
 import torch
 from million_b200 import ops, _lib
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 8

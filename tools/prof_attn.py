@@ -1,6 +1,6 @@
 """Tiny driver for ncu: a few decode-attention launches on Llama-3.1-8B shapes (one layer), then CUDA-event timing."""
 import argparse, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("MILLION_PKG_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # MILLION_PKG_ROOT: A/B against another tree (e.g. variants/r1)
 import torch
 from million_b200 import ops
 
