@@ -19,6 +19,13 @@
 // Replaces Interface.cu:49-118 + Kernel.cuh:11-166, 1038-1209, 1211-1270 of the reference.
 #include "attn_fast_helpers.cuh"
 
+// Tiles between two flushes of the packed-half PV sums into fp32.  1 = every tile (16 terms per lane): measured FASTER than 2
+// (97.5 vs 99.6 us per launch at batch 8, A/B on one box: the flush code replaces the counter's branch) and it halves the
+// life of the half sums; tools/precision_budget.py shows the sums are not what limits accuracy either way.
+#ifndef MILLION_PV_FLUSH_TILES
+#define MILLION_PV_FLUSH_TILES 1
+#endif
+
 namespace million {
 
 
@@ -462,7 +469,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             }
             __syncwarp();                                   // every lane is done with the V tile and the p slots
             issue_v(tile + kWarps);                          // V(i+1) streams in during the next QK phase
-            if (++since_flush == 2) {                       // packed-half partial sums live for at most 2 tiles (32 terms)
+            if (++since_flush == MILLION_PV_FLUSH_TILES) {   // packed-half partial sums live for MILLION_PV_FLUSH_TILES tiles (16 terms per lane each)
 #pragma unroll
                 for (int sl = 0; sl < 4; ++sl)
 #pragma unroll
@@ -703,8 +710,8 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
         MILLION_UNSUPPORTED("fast decode attention: paged V needs page_size %% 32 == 0 and an aligned pool");
     if (a.nk > 0 && a.v_layout == MILLION_V_TRANSPOSED && ((a.v_ld & 15) || (a.v_head_stride & 15) || ((uintptr_t)a.v_codes & 15)))
         MILLION_UNSUPPORTED("fast decode attention: transposed V needs 16-byte aligned rows");
-    if (a.nk > 0 && a.v_out > 0 && (dm4 || Gfull > 2 || a.v_out > 4))
-        MILLION_UNSUPPORTED("fast decode attention: V-side outlier records need M=64, nh/nh_k <= 2 and v_out <= 4 (the generic kernel runs the rest)");
+    if (a.nk > 0 && a.v_out > 0 && ((!dm4 && Gfull > 2) || a.v_out > 4))
+        MILLION_UNSUPPORTED("fast decode attention: V-side outlier records need v_out <= 4 and, at M=64, nh/nh_k <= 2 (no shared memory left at 4 heads per CTA; the generic kernel runs the rest)");
     if (a.nk > 0 && a.v_out > 0 && a.v_out != 3 &&
         ((uintptr_t)a.vo_idx % a.v_out || a.vo_head_stride % a.v_out || (uintptr_t)a.vo_val % (2 * a.v_out)))
         MILLION_UNSUPPORTED("fast decode attention: the V-side outlier store must be aligned to one token's records");

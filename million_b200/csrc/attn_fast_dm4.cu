@@ -57,6 +57,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
     unsigned char* stage_p = smem + kStageOff;                           // kWarps * (K tile + V tile) = 16 KB used in the main loop
     unsigned char* pbuf_p = smem + kPbufOff;
     int* flag = reinterpret_cast<int*>(smem + kMiscOff);
+    float* vo_acc = reinterpret_cast<float*>(smem + kMiscOff + 1024) + (threadIdx.x >> 5) * (G * 128);   // OUT & 2: this warp's V-outlier sums [g][dim]
     float* xch = reinterpret_cast<float*>(stage_p);                      // 2 * kWarps entries, then kMergeScratch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -116,7 +117,10 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             __syncthreads();
             if (ch + 2 < 4) load_chunk(ch + 2);
         }
-        if constexpr (OUT) {
+        if constexpr ((OUT & 2) != 0) {
+            for (int i = (threadIdx.x & 31); i < G * 128; i += 32) vo_acc[i] = 0.f;
+        }
+        if constexpr ((OUT & 1) != 0) {
             // q as a [dim][head] table for the outlier terms (misc area; flag and merge scratch there are used after the loop)
             T* qt = reinterpret_cast<T*>(smem + kMiscOff);
             for (int i = tid; i < 128 * G; i += kThreads)
@@ -208,8 +212,19 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
         // Raw load results only: nothing consumes them before the next iteration (a shift or an OR here would make this warp wait
         // for the HBM round trip on the spot).  k_out 1, 2, 4: one vector load each for dims and deltas; 3: byte-wise.
         uint32_t ko_dims = 0, ko_v01 = 0, ko_v23 = 0;
+        // V-side records (OUT bit 1), same prefetch; applied in the QK phase where a lane is its token (see attn_fast.cu)
+        uint32_t vo_dims = 0, vo_v01 = 0, vo_v23 = 0;
+        auto vo_fetch = [&](int tile) {
+            if constexpr ((OUT & 2) != 0) {
+                const int tok = t0 + tile * kTile + lane;
+                const bool ok = tile < n_tiles && tok < t1;
+                const int64_t rec = hb * a.vo_head_stride + (int64_t)(ok ? tok : t0) * a.v_out;
+                ko_load(a.vo_idx + rec, reinterpret_cast<const unsigned short*>(a.vo_val) + rec, a.v_out, vo_dims, vo_v01, vo_v23);
+            }
+        };
+        vo_fetch(warp);
         auto ko_fetch = [&](int tile) {
-            if constexpr (OUT) {
+            if constexpr ((OUT & 1) != 0) {
                 const int tok = t0 + tile * kTile + lane;
                 const bool ok = tile < n_tiles && tok < t1;
                 const int64_t rec = hb * a.ko_head_stride + (int64_t)(ok ? tok : t0) * a.k_out;
@@ -226,6 +241,8 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             const bool valid = tok < t1;
             const uint32_t my_dims = ko_dims, my_v01 = ko_v01, my_v23 = ko_v23;
             ko_fetch(tile + kWarps);
+            const uint32_t my_vdims = vo_dims, my_vv01 = vo_v01, my_vv23 = vo_v23;
+            vo_fetch(tile + kWarps);
 
             // ------------------------------------------------ QK: 32 conflict-free LUT gathers for my token
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -243,7 +260,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                     if constexpr (G == 4) fhadd2(s4[2], s4[3], e.y);
                 }
             }
-            if constexpr (OUT) {
+            if constexpr ((OUT & 1) != 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (i < a.k_out) {
@@ -289,6 +306,11 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                         for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
                             for (int k = 0; k < 4; ++k) out_o[sl][g][k] *= alpha;
+                        if constexpr ((OUT & 2) != 0) {      // warp-uniform branch
+                            __syncwarp();
+                            for (int i = lane; i < 128; i += 32) vo_acc[g * 128 + i] *= alpha;
+                            __syncwarp();
+                        }
                         run_m[g] = nm;
                     }
                 }
@@ -298,6 +320,18 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             for (int g = 0; g < G; ++g) {
                 p[g] = exp2_safe(s[g], run_m[g]);
                 run_l[g] += p[g];
+            }
+            if constexpr ((OUT & 2) != 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < a.v_out) {
+                        const uint32_t pair = i < 2 ? my_vv01 : my_vv23;
+                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : (pair & 0xffffu));
+                        const float dv = valid ? io<T>::to_f(*reinterpret_cast<const T*>(&hv)) : 0.f;
+                        const int dim = (my_vdims >> (8 * i)) & 0xff;
+#pragma unroll
+                        for (int g = 0; g < G; ++g) atomicAdd(vo_acc + g * 128 + dim, p[g] * dv);
+                    }
             }
             *reinterpret_cast<uint2*>(pbuf_w + lane * 8) = make_uint2(as_u32(__floats2half2_rn(p[0], p[1])), as_u32(__floats2half2_rn(p[2], p[3])));
 
@@ -403,7 +437,11 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                 for (int k = 0; k < 4; ++k) {
                     // both half-warps use the same slot -> sub-space map; fold hw=1 into hw=0
                     const float theirs = __shfl_xor_sync(0xffffffffu, out_o[sl][g][k], 16);
-                    if (hw == 0) wx[g * 128 + 4 * (2 * lq + ((sl + lq) & 1)) + k] = out_o[sl][g][k] + theirs;
+                    if (hw == 0) {
+                        float v = out_o[sl][g][k] + theirs;
+                        if constexpr ((OUT & 2) != 0) { if (t1 > t0) v += vo_acc[g * 128 + 4 * (2 * lq + ((sl + lq) & 1)) + k]; }
+                        wx[g * 128 + 4 * (2 * lq + ((sl + lq) & 1)) + k] = v;
+                    }
                 }
         float* ww = xch + (kWarps + warp) * kEntry;
 #pragma unroll
@@ -478,7 +516,7 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_dm4_kernel(const 
 template <typename T, int G, int OUT>
 static int launch_dm4_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
-    const size_t smem = dm4::kLutBytes + kVtabBytes + 32768 + 3072 + kWarps * kTile * 8 + (OUT ? 1024 : 256);
+    const size_t smem = dm4::kLutBytes + kVtabBytes + 32768 + 3072 + kWarps * kTile * 8 + (OUT ? 1024 : 256) + ((OUT & 2) ? kWarps * G * 128 * 4 : 0);
     static_assert(32768 + 3072 >= 2 * kWarps * 4 * 130 * sizeof(float) + 64, "stage area too small for the combine");
     static_assert(32768 + 3072 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static SmemAttrOnce configured = {};
@@ -491,14 +529,23 @@ static int launch_dm4_t(const AttnArgs& a, const uint32_t* prepared, int gsub, c
 
 int launch_attn_fast_dm4(const AttnArgs& a, int io_dtype, int G, int gsub, const void* prepared, cudaStream_t stream) {
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
-    if (io_dtype == MILLION_F16) {
-        if (G == 4) return (a.k_out ? launch_dm4_t<__half, 4, 1>(a, prep, gsub, stream) : launch_dm4_t<__half, 4, 0>(a, prep, gsub, stream));
-        if (G == 2) return (a.k_out ? launch_dm4_t<__half, 2, 1>(a, prep, gsub, stream) : launch_dm4_t<__half, 2, 0>(a, prep, gsub, stream));
-        return (a.k_out ? launch_dm4_t<__half, 1, 1>(a, prep, gsub, stream) : launch_dm4_t<__half, 1, 0>(a, prep, gsub, stream));
+    const int kv = (a.nk > 0 && a.k_out ? 1 : 0) | (a.nk > 0 && a.v_out ? 2 : 0);     // outlier side stores: bit 0 K, bit 1 V
+#define MILLION_DM4_CASE(TT, GG)                                                  \
+    switch (kv) {                                                                 \
+        case 0: return launch_dm4_t<TT, GG, 0>(a, prep, gsub, stream);            \
+        case 1: return launch_dm4_t<TT, GG, 1>(a, prep, gsub, stream);            \
+        case 2: return launch_dm4_t<TT, GG, 2>(a, prep, gsub, stream);            \
+        default: return launch_dm4_t<TT, GG, 3>(a, prep, gsub, stream);           \
     }
-    if (G == 4) return (a.k_out ? launch_dm4_t<__nv_bfloat16, 4, 1>(a, prep, gsub, stream) : launch_dm4_t<__nv_bfloat16, 4, 0>(a, prep, gsub, stream));
-    if (G == 2) return (a.k_out ? launch_dm4_t<__nv_bfloat16, 2, 1>(a, prep, gsub, stream) : launch_dm4_t<__nv_bfloat16, 2, 0>(a, prep, gsub, stream));
-    return (a.k_out ? launch_dm4_t<__nv_bfloat16, 1, 1>(a, prep, gsub, stream) : launch_dm4_t<__nv_bfloat16, 1, 0>(a, prep, gsub, stream));
+    if (io_dtype == MILLION_F16) {
+        if (G == 4) MILLION_DM4_CASE(__half, 4)
+        if (G == 2) MILLION_DM4_CASE(__half, 2)
+        MILLION_DM4_CASE(__half, 1)
+    }
+    if (G == 4) MILLION_DM4_CASE(__nv_bfloat16, 4)
+    if (G == 2) MILLION_DM4_CASE(__nv_bfloat16, 2)
+    MILLION_DM4_CASE(__nv_bfloat16, 1)
+#undef MILLION_DM4_CASE
 }
 
 }  // namespace million
