@@ -35,15 +35,19 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str = None) -> str:
+    """`out`: build a VARIANT (MILLION_NVCC_EXTRA switches) into that path, with its own object directory, leaving the in-tree
+    library and its stamp alone (A/B runs: MILLION_B200_LIB=variants/x.so)."""
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+    variant = out is not None
+    out = out or OUT
+    if not variant and not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build") if not variant else out + ".build"
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in sources():
@@ -53,21 +57,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     log = []
     for src, p in procs:
-        out, _ = p.communicate()
-        log.append(f"== {os.path.basename(src)}\n{out}")
+        text, _ = p.communicate()
+        log.append(f"== {os.path.basename(src)}\n{text}")
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcuda"]
+    link = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcuda"]
     subprocess.check_call(link)
     with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
-    with open(STAMP, "w") as f:
-        f.write(dig)
+    if not variant:
+        with open(STAMP, "w") as f:
+            f.write(dig)
     if verbose:
         print("\n".join(log))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out))

@@ -22,12 +22,16 @@
 // Tiles between two flushes of the packed-half PV sums into fp32.  1 = every tile (16 terms per lane): measured FASTER than 2
 // (97.5 vs 99.6 us per launch at batch 8, A/B on one box: the flush code replaces the counter's branch) and it halves the
 // life of the half sums; tools/precision_budget.py shows the sums are not what limits accuracy either way.
+#ifndef MILLION_PV_UNROLL
+#define MILLION_PV_UNROLL 8      // PV loop (8 steps of 2 tokens per half-warp) fully unrolled: 95.7 us per launch at batch 8 vs 96.8 (4), 97.4 (2), 105.9 (1) — profiles/r02_ab_variants.txt
+#endif
 #ifndef MILLION_PV_FLUSH_TILES
 #define MILLION_PV_FLUSH_TILES 1
 #endif
 
 namespace million {
 
+constexpr int kPvUnroll = MILLION_PV_UNROLL;
 
 // ------------------------------------------------------------------------------------------------
 // Codebook preparation (once per codebook): fp16 tables in the column order the kernel gathers with.
@@ -414,7 +418,7 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
                 // from the other half-warp's: conflict free); the p slots of those two tokens are adjacent (see p_slot), so ONE
                 // 16-byte broadcast load brings both.
                 if (!MILLION_DBG_MODE(a, 2))
-#pragma unroll 2
+#pragma unroll kPvUnroll
                 for (int jq = 0; jq < kTile / 4; ++jq) {
                     const uint4 pk = lds128(pbuf_w, (4 * jq + 2 * hw) * 8);
                     uint32_t word[2];
@@ -514,7 +518,10 @@ __device__ __forceinline__ void attn_fast_segment(const AttnArgs& a, const uint3
             }
             // kWinBatch tokens per round: all their row loads are in flight together (a dependent load per token put ~1 us of loaded-memory
             // latency on every one of them: 6.5 us per CTA at 32K, batch 8), then one softmax update per head for the whole round
-            constexpr int kWinBatch = 4;
+#ifndef MILLION_WIN_BATCH
+#define MILLION_WIN_BATCH 4
+#endif
+            constexpr int kWinBatch = MILLION_WIN_BATCH;
             for (int tb = w0 + warp; tb < w1; tb += kWinBatch * kWarps) {
                 uint2 kr[kWinBatch], vr[kWinBatch];
 #pragma unroll

@@ -13,8 +13,14 @@ constexpr int kTile = 32;                       // tokens per warp tile
 constexpr int kRowBytes = 64;                   // M = 64 one-byte codes
 constexpr int kStageBytes = 2 * kTile * kRowBytes;   // one K tile + one V tile per warp
 constexpr int kVtabBytes = 64 * 1024;
-constexpr int kFlatPad = 24;                    // cost of one more (prologue + epilogue) in 64-token units (~9 us)
-constexpr float kRescaleMargin = 6.f;           // log2 units: p <= 64 before a rescale is forced
+#ifndef MILLION_FLAT_PAD
+#define MILLION_FLAT_PAD 24
+#endif
+constexpr int kFlatPad = MILLION_FLAT_PAD;      // cost of one more (prologue + epilogue) in 64-token units
+#ifndef MILLION_RESCALE_MARGIN
+#define MILLION_RESCALE_MARGIN 6.f
+#endif
+constexpr float kRescaleMargin = MILLION_RESCALE_MARGIN;   // log2 units: p <= 64 before a rescale is forced
 
 template <int G> struct LutCfg;
 template <> struct LutCfg<4> { static constexpr int bytes = 128 * 1024; };

@@ -37,3 +37,12 @@ if m.any():
     print(f"  merging pieces ({int(m.sum())}): total {((tt[:, 6] - tt[:, 5]).mean()) / 1e3:.2f} us = call+issue {(tt[:, 11] - tt[:, 5]).mean() / 1e3:.2f}, wait {(tt[:, 12] - tt[:, 11]).mean() / 1e3:.2f}, "
           f"m/l {(tt[:, 9] - tt[:, 12]).mean() / 1e3:.2f}, weights {(tt[:, 10] - tt[:, 9]).mean() / 1e3:.2f}, sum+store {(tt[:, 6] - tt[:, 10]).mean() / 1e3:.2f}")
 print(f"  start skew max {(t[:, 0, 0].max() - t0) / 1e3:.2f} us; end mean {(end - t0).mean() / 1e3:.1f} min {(end - t0).min() / 1e3:.1f} max {(end - t0).max() / 1e3:.1f} us")
+# where the tail skew comes from: CTAs by number of pieces (a run that crosses a group boundary pays a second prologue/epilogue)
+ml = torch.where(t[:, :, 0] > 0, t[:, :, 2] - t[:, :, 1], torch.zeros(())).sum(1)
+fx = (end - t[:, 0, 0]) - ml
+for p in sorted(set(pieces.tolist())):
+    sel = pieces == p
+    print(f"  CTAs with {int(p)} piece(s): {int(sel.sum()):3d}; end mean {(end[sel] - t0).mean() / 1e3:6.1f} (min {(end[sel] - t0).min() / 1e3:6.1f}, max {(end[sel] - t0).max() / 1e3:6.1f}) us; "
+          f"main loop mean {ml[sel].mean() / 1e3:6.1f} (min {ml[sel].min() / 1e3:6.1f}, max {ml[sel].max() / 1e3:6.1f}); everything else {fx[sel].mean() / 1e3:5.1f} us")
+q10 = torch.quantile(end - t0, torch.tensor([0.1, 0.5, 0.9], dtype=torch.float64)) / 1e3
+print(f"  end time quantiles 10/50/90 %: {q10[0]:.1f} / {q10[1]:.1f} / {q10[2]:.1f} us")
