@@ -218,9 +218,10 @@ typedef struct million_attn_params {
     int64_t v_out_head_stride;
 
     /* Split-KV across GPUs fused into this launch (MILLION_ATTN_FUSED_SPLITKV): instead of returning the rank's partial state,
-     * the last CTA of every (b, kv-head) group stores the group's rows straight into every peer's symmetric buffer over NVLink,
-     * publishes a per-(rank, group) sequence flag, waits for the peers' flags of ITS group (bounded spin) and writes the merged
-     * rows to `out` — one launch per layer, no cross-group serialisation.  Same buffers as million_splitkv_push_merge
+     * the last CTA of every (b, kv-head) group stores the group's rows straight into every peer's symmetric buffer over NVLink
+     * as 8-byte cells {value, sequence number} (data and validity in one store: no fence, no flag), spins on the peers' cells of
+     * ITS group (bounded) and writes the merged rows to `out` — one launch per layer, no cross-group serialisation, exchange
+     * latency = one store's flight time.  Same buffers as million_splitkv_push_merge
      * (rows = bs * nh); `p2p_state` is the million_splitkv_state_bytes() block prepared once by million_splitkv_state_init.
      * Compiled for the fast kernel at M = 64, nh/nh_k = 4, row-major value codes, no side store; MILLION_ERR_UNSUPPORTED otherwise.
      * If a wait gives up (dead peer), the affected rows are NaN and the error word of the state block is set. */

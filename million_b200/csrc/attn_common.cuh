@@ -115,10 +115,33 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
 }
 
 // Symmetric buffer of the split-KV exchange (same layout on every rank; million_splitkv_symmetric_bytes):
-//   [0, 1024)            per-source-rank flags of million_splitkv_push_merge: rank g at byte 128*g (u32 sequence number)
-//   [1024, 1024 + 8192)  per-(source rank, group) flags of the exchange fused into the attention kernel: u32 at (g*256 + group)*4
-//   [9216, ...)          recv[parity 2][world][rows][d+2] fp32
-constexpr int kP2PGroupFlagOff = 1024, kP2PMaxGroups = 256, kP2PRecvOff = 1024 + 8 * kP2PMaxGroups * 4;
+//   [0, 1024)        per-source-rank flags of million_splitkv_push_merge: rank g at byte 128*g (u32 sequence number)
+//   [1024, ...)      recv[parity 2][world][rows][d+2] fp32 (million_splitkv_push_merge)
+//   [p2p_ll_offset)  the same layout in tagged 8-byte cells (exchange fused into the attention kernel)
+constexpr int kP2PRecvOff = 1024;
+// The exchange fused into the attention kernel uses a second receive area right behind the first: the same
+// [parity][world][rows][d+2] layout in 8-byte cells {fp32 value, u32 sequence number}.  A value and the tag that validates it
+// travel in ONE 8-byte store, so the receiver polls the data itself: no release fence (a round trip over NVLink before a flag
+// may be published), no flag — the latency of the exchange is one store's flight time (the idea of NCCL's LL protocol).
+__host__ __device__ __forceinline__ constexpr int64_t p2p_ll_offset(int world, int64_t rows, int d) {
+    return kP2PRecvOff + (int64_t)2 * world * rows * (d + 2) * 4;
+}
+__device__ __forceinline__ void st_tagged(float* cell, float v, unsigned tag) {
+    asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(cell), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+// spins until the cell carries `tag`; false if `limit` polls (100 ns apart) went by
+__device__ __forceinline__ bool ld_tagged(const float* cell, unsigned tag, int limit, float& v) {
+    unsigned bits, t;
+    int spins = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(bits), "=r"(t) : "l"(cell) : "memory");
+        if (t == tag) break;
+        __nanosleep(100);
+        if (++spins > limit) { v = __int_as_float(0x7fc00000); return false; }
+    }
+    v = __uint_as_float(bits);
+    return true;
+}
 
 // device-memory block of the split-KV protocol (million_splitkv_state_init): read only on the merge path
 struct P2PState {
@@ -286,10 +309,11 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
                 // fused split-KV: this rank's state of row (b, h) goes straight into slot [parity][rank] of EVERY rank's receive
                 // buffer (NVLink stores, consecutive k = coalesced); layout of million_splitkv_push_merge
                 const size_t off = ((size_t)p2p_par * p2p_world + p2p_rank) * p2p_slot + (size_t)(b * a.nh + h) * ostride;
+                const int64_t ll_off = p2p_ll_offset(p2p_world, p2p_rows, a.d);
                 for (int r = 0; r < p2p_world; ++r) {
-                    float* dst = reinterpret_cast<float*>(ps->peer[r] + kP2PRecvOff) + off;
-                    dst[k] = acc;
-                    if (k == 0) { dst[a.d] = hd[2 * g] * kLn2; dst[a.d + 1] = hd[2 * g + 1]; }
+                    float* dst = reinterpret_cast<float*>(ps->peer[r] + ll_off) + 2 * off;       // 8-byte cells {value, sequence tag}
+                    st_tagged(dst + 2 * k, acc, p2p_seq);
+                    if (k == 0) { st_tagged(dst + 2 * a.d, hd[2 * g] * kLn2, p2p_seq); st_tagged(dst + 2 * (a.d + 1), hd[2 * g + 1], p2p_seq); }
                 }
             } else if (a.partial_out) {
                 a.partial_out[(int64_t)(b * a.nh + h) * ostride + k] = acc;
@@ -305,37 +329,29 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
         __syncthreads();
     }
     if constexpr (P2P) {
-        // ---------------------------------------------------------------- publish this group, wait for the peers' rows of it, final merge
-        // Ordering: the block's peer stores -> bar.sync -> release stores of the group flag at system scope (one thread per
-        // destination; release is cumulative over what the barrier ordered before it) -> the peers' acquire loads.
-        const int grp = b * a.nh_k + hk;
-        __syncthreads();
-        int* sflag = reinterpret_cast<int*>(scr);
-        if (threadIdx.x == 0) *sflag = 0;
-        __syncthreads();
-        if ((int)threadIdx.x < p2p_world) {
-            st_release_sys(reinterpret_cast<unsigned*>(ps->peer[threadIdx.x] + kP2PGroupFlagOff) + p2p_rank * kP2PMaxGroups + grp, p2p_seq);
-            const unsigned* f = reinterpret_cast<const unsigned*>(ps->peer[p2p_rank] + kP2PGroupFlagOff) + threadIdx.x * kP2PMaxGroups + grp;
-            const int limit = ps->spin_limit > 0 ? ps->spin_limit : kP2PDefaultSpins;
-            int spins = 0;
-            while ((int)(ld_acquire_sys(f) - p2p_seq) < 0) {      // bounded: a dead peer must not hang the GPU
-                __nanosleep(100);
-                if (++spins > limit) { ps->err = 1; *sflag = 1; break; }
-            }
-        }
-        __syncthreads();
-        const bool timed_out = *sflag != 0;
-        // G rows x world parts, all from this rank's own receive buffer: (1) the (m, l) pairs, (2) weights, (3) outputs
-        const float* recv = reinterpret_cast<const float*>(ps->peer[p2p_rank] + kP2PRecvOff) + (size_t)p2p_par * p2p_world * p2p_slot;
+        // ---------------------------------------------------------------- wait for the peers' rows of THIS group, final merge
+        // No flag and no fence: every 8-byte cell carries the sequence number of the call that wrote it, the threads below spin on
+        // the cells they need (all in this rank's own receive area).  (1) the (m, l) pairs of G rows x world parts, (2) weights,
+        // (3) the outputs.
+        const int limit = ps->spin_limit > 0 ? ps->spin_limit : kP2PDefaultSpins;
+        const float* recv = reinterpret_cast<const float*>(ps->peer[p2p_rank] + p2p_ll_offset(p2p_world, p2p_rows, a.d)) +
+                            2 * ((size_t)p2p_par * p2p_world * p2p_slot);
         const int W = p2p_world, os = a.d + 2, row0 = b * a.nh + hk * G;
+        int* sflag = reinterpret_cast<int*>(scr);
         float* sm_m = scr + 64;            // [G][W]   (G * W <= 8 * 64 fits the 2048-float blocks with room to spare)
         float* sm_l = scr + 2048;
         float* sm_w = scr + 4096;
+        __syncthreads();                   // the group merge above is done with the scratch
+        if (threadIdx.x == 0) *sflag = 0;
+        __syncthreads();
         for (int i = threadIdx.x; i < G * W; i += blockDim.x) {
             const int g = i / W, w = i - g * W;
-            const float* p = recv + (size_t)w * p2p_slot + (size_t)(row0 + g) * os;
-            sm_m[i] = __ldcg(p + a.d);
-            sm_l[i] = __ldcg(p + a.d + 1);
+            const float* p = recv + 2 * ((size_t)w * p2p_slot + (size_t)(row0 + g) * os);
+            float m, l;
+            const bool ok = ld_tagged(p + 2 * a.d, p2p_seq, limit, m) & ld_tagged(p + 2 * (a.d + 1), p2p_seq, limit, l);
+            if (!ok) { ps->err = 1; *sflag = 1; }
+            sm_m[i] = m;
+            sm_l[i] = l;
         }
         __syncthreads();
         for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -352,13 +368,20 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
             for (int w = 0; w < W; ++w) sm_w[g * W + w] *= inv;
         }
         __syncthreads();
+        const bool ml_timed_out = *sflag != 0;
         for (int i = threadIdx.x; i < G * a.d; i += blockDim.x) {
             const int g = i / a.d, k = i - g * a.d;
-            const float* p = recv + (size_t)(row0 + g) * os + k;
+            const float* p = recv + 2 * ((size_t)(row0 + g) * os + k);
             float acc = 0.f;
-            for (int w = 0; w < W; ++w) acc = fmaf(__ldcg(p + (size_t)w * p2p_slot), sm_w[g * W + w], acc);
+            bool ok = !ml_timed_out;
+            for (int w = 0; w < W && ok; ++w) {
+                float v;
+                ok = ld_tagged(p + 2 * (size_t)w * p2p_slot, p2p_seq, limit, v);
+                acc = fmaf(v, sm_w[g * W + w], acc);
+            }
+            if (!ok) ps->err = 1;
             // a wait that gave up must not pass stale rows on as a result: poison them (and P2PState.err is set)
-            reinterpret_cast<T*>(a.out)[(size_t)(row0 + g) * a.d + k] = io<T>::from_f(timed_out ? __int_as_float(0x7fc00000) : acc);
+            reinterpret_cast<T*>(a.out)[(size_t)(row0 + g) * a.d + k] = io<T>::from_f(ok ? acc : __int_as_float(0x7fc00000));
         }
         // off the critical path: the last group of the launch advances the call counter (every group-last CTA of the NEXT launch
         // reads it after that launch's dependency on this one is resolved)

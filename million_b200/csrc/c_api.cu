@@ -247,7 +247,6 @@ int million_pq_decode_attn(const million_attn_params* p, million_stream_t stream
     const bool partial_only = (p->flags & MILLION_ATTN_PARTIAL_ONLY) != 0;
     const bool fused_splitkv = (p->flags & MILLION_ATTN_FUSED_SPLITKV) != 0;
     MILLION_REQUIRE(!(partial_only && fused_splitkv), "attn: PARTIAL_ONLY and FUSED_SPLITKV exclude each other");
-    if (fused_splitkv) MILLION_REQUIRE((int64_t)p->bs * p->nh_k <= kP2PMaxGroups, "attn: fused split-KV serves at most %d (batch, kv-head) groups", kP2PMaxGroups);
     if (fused_splitkv) MILLION_REQUIRE(p->out != nullptr, "attn: fused split-KV writes the merged result to `out`");
     if (fused_splitkv) MILLION_REQUIRE(p->p2p_state != nullptr && ((uintptr_t)p->p2p_state & 15) == 0, "attn: fused split-KV needs the (16-byte aligned) state block of million_splitkv_state_init");
     MILLION_REQUIRE(p->q && p->k_cent && p->v_cent && p->workspace, "attn: null pointer");

@@ -119,7 +119,7 @@ using namespace million;
 extern "C" {
 
 int64_t million_splitkv_symmetric_bytes(int world, int64_t rows, int d) {
-    return kP2PRecvOff + (int64_t)2 * world * rows * (d + 2) * 4;
+    return p2p_ll_offset(world, rows, d) + (int64_t)2 * world * rows * (d + 2) * 8;      // flags | fp32 receive area | tagged 8-byte cells
 }
 
 // every block of the exchange kernel spins until all ranks have published: the whole grid must be co-resident
