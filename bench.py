@@ -366,13 +366,16 @@ def splitkv_128k(torch, dist, ops, T, world, rank, device, peak, steps):
     kc_full = torch.randint(0, C, (1, NH_K, nk, M), dtype=torch.uint8, device=device, generator=g)
     vc_full = torch.randint(0, C, (1, NH_K, nk, M), dtype=torch.uint8, device=device, generator=g)
     s, e = sharding.split_kv_ranges(nk, world)[rank]
-    r_local = r if rank == world - 1 else 0
-    res = {"ctx": ctx, "bs": 1, "layers": LAYERS, "scaling": "strong", "tokens_per_rank": e - s}
+    # the window is replicated (every rank has the new token's k/v under tensor parallelism) and dealt out row-wise, so no rank
+    # carries it alone: views of the same buffers, r_local rows from w0 on
+    w0, w1 = sharding.split_window_rows(r, world, rank)
+    kres_l, vres_l, r_local = kres[:, :, w0:], vres[:, :, w0:], w1 - w0
+    res = {"ctx": ctx, "bs": 1, "layers": LAYERS, "scaling": "strong", "tokens_per_rank": e - s, "window_rows_per_rank": r_local}
     single = ops.pq_decode_attn(q, kc_full, vc_full, kcent, vcent, kres, vres, r)
     alg = algorithmic_bytes(1, nk, r)
     if world > 1:
         peer = sharding.SplitKVPeerGroup(NH, D, torch.float16)
-        merged = peer.decode_attn(q, kc_full[:, :, s:e].contiguous(), vc_full[:, :, s:e].contiguous(), kcent, vcent, kres, vres, r_local).clone()
+        merged = peer.decode_attn(q, kc_full[:, :, s:e].contiguous(), vc_full[:, :, s:e].contiguous(), kcent, vcent, kres_l, vres_l, r_local).clone()
         err = torch.tensor([(merged.float() - single.float()).abs().max().item()], device=device)
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         res["max_abs_merged_minus_single_gpu"] = float(err.item())
@@ -383,9 +386,9 @@ def splitkv_128k(torch, dist, ops, T, world, rank, device, peak, steps):
         for name, fused, pdl in (("two_launches", False, False), ("two_launches_pdl", False, True), ("fused", True, False), ("fused_pdl", True, True)):
             def step():
                 for k_, v_ in local:
-                    peer.decode_attn(q, k_, v_, kcent, vcent, kres, vres, r_local, out=out, fused=fused, pdl=pdl)
+                    peer.decode_attn(q, k_, v_, kcent, vcent, kres_l, vres_l, r_local, out=out, fused=fused, pdl=pdl)
             try:
-                chk = peer.decode_attn(q, kc_full[:, :, s:e].contiguous(), vc_full[:, :, s:e].contiguous(), kcent, vcent, kres, vres, r_local, fused=fused, pdl=pdl)
+                chk = peer.decode_attn(q, kc_full[:, :, s:e].contiguous(), vc_full[:, :, s:e].contiguous(), kcent, vcent, kres_l, vres_l, r_local, fused=fused, pdl=pdl)
                 verr = torch.tensor([(chk.float() - single.float()).abs().max().item()], device=device)
                 dist.all_reduce(verr, op=dist.ReduceOp.MAX)
                 graph = capture(torch, step, warm=2)

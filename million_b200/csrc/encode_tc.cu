@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a)
     uint64_t* bars = reinterpret_cast<uint64_t*>(Zs + kZeroBytes);   // 2 warpgroups * 2 halves
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     float* cmax_s = reinterpret_cast<float*>(tmem_slot + 2);    // kMG floats
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(cmax_s + kMG);    // arrival of the B tiles (one TMA bulk copy)
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int wg = warp >> 2, row = tid & 127;                  // warpgroup, token row inside the tile
@@ -186,20 +187,28 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncArgs a)
     if (tid == 32) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_init(smem_u32(bar_b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // The B operand — this CTA's kMG codebook tiles [-2c | |c|^2 split], 64 KB contiguous in the prepared buffer — comes in
+        // with ONE TMA bulk copy (cp.async.bulk, async proxy end to end: no generic-proxy stores, no proxy fence for B).  The
+        // tensor-map form of TMA has nothing to add for a contiguous block; the A rows cannot be copied at all, they are
+        // synthesised ([x, 1, 1, 1, 0..] per token).
+        constexpr uint32_t kBBytes = kMG * kBTileBytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_b)), "r"(kBBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(Bs)),
+                     "l"(a.prep + (int64_t)m0 * kBTileBytes), "r"(kBBytes), "r"(smem_u32(bar_b))
+                     : "memory");
     }
     {
-        const uint4* src = reinterpret_cast<const uint4*>(a.prep + (int64_t)m0 * kBTileBytes);
-        uint4* dstB = reinterpret_cast<uint4*>(Bs);
-        for (int i = tid; i < kMG * kBTileBytes / 16; i += kThreads) dstB[i] = __ldg(src + i);
         uint4* z = reinterpret_cast<uint4*>(Zs);
         for (int i = tid; i < kZeroBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         if (tid < kMG) cmax_s[tid] = reinterpret_cast<const float*>(a.prep + (int64_t)a.M * kBTileBytes)[m0 + tid];
     }
-    fence_async_proxy();        // generic-proxy writes (B, zeros) -> visible to the tensor core's async proxy
+    fence_async_proxy();        // generic-proxy writes (zeros) -> visible to the tensor core's async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mbar_wait(smem_u32(bar_b), 0);   // the B tiles have landed
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t zs = smem_u32(Zs);
     const uint32_t bar0 = smem_u32(&bars[wg * 2]), bar1 = bar0 + 8;
@@ -409,7 +418,7 @@ int launch_encode_tc_prepare(const float* cent, int x_dtype, int d, int M, int C
 
 template <typename T, int DM>
 static int launch_tc_t(const tc::EncArgs& a, cudaStream_t stream) {
-    const size_t smem = tc::kMG * tc::kBTileBytes + 4 * tc::kATileBytes + tc::kZeroBytes + 32 + 16 + tc::kMG * 4 + 64;
+    const size_t smem = tc::kMG * tc::kBTileBytes + 4 * tc::kATileBytes + tc::kZeroBytes + 32 + 16 + tc::kMG * 4 + 8 + 64;
     static SmemAttrOnce configured = {};
     MILLION_CUDA_OK(ensure_dynamic_smem(configured, tc::encode_tc_kernel<T, DM>, smem));
     const int ygroups = a.M / tc::kMG;

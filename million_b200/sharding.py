@@ -8,7 +8,7 @@ The reference is single-GPU (scripts/modeldb/main_pq.py:74 "TODO: support multi-
     un-normalised (o, m, l) state of its range with the same kernel (MILLION_ATTN_PARTIAL_ONLY), the states are
     all-gathered (bs*nh*(d+2) fp32 = 16.6 KB per rank for Llama-3.1-8B shapes) over NCCL/NVLink and merged with the
     log-sum-exp algebra of flash_decoding_reduce_kernel (scripts/modeldb/bindings/Kernel.cuh:1249-1269).
-    The fp16 window lives on the last rank.
+    The fp16 window lives on the last rank, or — balanced — is replicated and dealt out row-wise (split_window_rows).
 """
 from typing import List, Tuple
 
@@ -35,6 +35,13 @@ def split_kv_ranges(nk: int, world: int, page: int = 64) -> List[Tuple[int, int]
         out.append((min(p * page, nk), min((p + q) * page, nk)))
         p += q
     return out
+
+
+def split_window_rows(r: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows [start, end) of the r-row fp16 window that `rank` attends over when the window is replicated on every rank (each
+    rank computes the new token's k/v anyway under tensor parallelism) instead of living on the last rank only: the ranks'
+    work stays balanced, nobody waits for the one that also owns the window."""
+    return r * rank // world, r * (rank + 1) // world
 
 
 def allgather_partials(partial: torch.Tensor, group=None) -> torch.Tensor:

@@ -538,3 +538,31 @@ def make_inputs(*, bs, nh, nh_k, nk, d=128, M=64, C=256, Lt=128, seed=42, self_c
         kc = rng.integers(0, C, (bs, nh_k, nk, M), dtype=ct)
         vc = rng.integers(0, C, (bs, nh_k, nk, M), dtype=ct)
     return dict(q=q, kc=kc, vc=vc, kcent=kcent, vcent=vcent, kres=kres, vres=vres)
+
+
+# ----------------------------------------------------------------------------------------------
+# Codebook training.  The reference calls faiss (pq_utils.py:586-609: IndexPQ.train, niter 25); faiss is a
+# third-party dependency absent from the reference tree (faiss-cpu 1.9.0.post1, requirements.txt:18).  Restated here: ONE Lloyd
+# iteration of its per-sub-space k-means (assignment = fp32 squared-L2 arg-min, lowest index on ties — A.2; update = mean of the
+# assigned points, an empty cluster keeps its centroid).  Parity unpinned by the reference (no vectors, RNG not reproducible).
+
+
+def kmeans_step(X, cent):
+    """X (n, d) fp32, cent (M, C, dm) fp32 -> (new cent, codes (n, M), objective w.r.t. the old centroids, counts (M, C))."""
+    X = _f32(X)
+    cent = _f32(cent)
+    n, d = X.shape
+    M, C, dm = cent.shape
+    codes = pq_encode(X.reshape(1, 1, n, d), cent, out_dtype=np.uint8 if C <= 256 else np.uint16)[0, 0].astype(np.int64)
+    new = cent.copy()
+    counts = np.zeros((M, C), dtype=np.int64)
+    obj = 0.0
+    for m in range(M):
+        sub = X[:, m * dm:(m + 1) * dm]
+        obj += float(((sub - cent[m, codes[:, m]]) ** 2).sum(dtype=np.float64))
+        counts[m] = np.bincount(codes[:, m], minlength=C)
+        sums = np.zeros((C, dm), dtype=np.float64)
+        np.add.at(sums, codes[:, m], sub)
+        nz = counts[m] > 0
+        new[m, nz] = (sums[nz] / counts[m, nz, None]).astype(np.float32)
+    return new, codes, obj, counts
