@@ -11,7 +11,16 @@
 // Replaces Interface.cu:49-118 + Kernel.cuh:11-166, 1038-1209, 1211-1270 for the M=32 instantiations (setup.py:10-15).
 #include "attn_fast_helpers.cuh"
 
+#ifndef MILLION_DM4_PV_UNROLL
+#define MILLION_DM4_PV_UNROLL 16      // all 16 PV steps per tile: 86.3 us per launch (8B shapes, 32K, batch 8) vs 88.8 (8), 93.0 (4); flushing every tile: no gain here
+#endif
+#ifndef MILLION_DM4_FLUSH_TILES
+#define MILLION_DM4_FLUSH_TILES 2     // tiles between two flushes of the packed-half PV sums
+#endif
+
 namespace million {
+
+constexpr int kDm4PvUnroll = MILLION_DM4_PV_UNROLL;
 
 namespace dm4 {
 constexpr int kRow = 32;                               // bytes per token row
@@ -339,7 +348,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             __syncwarp();
 
             // ------------------------------------------------ PV: a half-warp per token, lane owns 2 sub-spaces (4 dims each)
-#pragma unroll 4
+#pragma unroll kDm4PvUnroll
             for (int jp = 0; jp < kTile / 2; ++jp) {
                 const int j = 2 * jp + hw;
                 const uint32_t pair = *reinterpret_cast<const unsigned short*>(vsp + j * dm4::kRow + lq * 2);
@@ -366,7 +375,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             }
             __syncwarp();
             issue(tile + kWarps, vbase, vs_s);
-            if (++since_flush == 2) { flush(); since_flush = 0; }
+            if (++since_flush == MILLION_DM4_FLUSH_TILES) { flush(); since_flush = 0; }
         }
         flush();
         cp_async_wait<0>();
