@@ -222,13 +222,16 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
         // for the HBM round trip on the spot).  k_out 1, 2, 4: one vector load each for dims and deltas; 3: byte-wise.
         uint32_t ko_dims = 0, ko_v01 = 0, ko_v23 = 0;
         // V-side records (OUT bit 1), same prefetch; applied in the QK phase where a lane is its token (see attn_fast.cu)
+        const bool ko_pair1 = (OUT & 1) != 0 && ko_pair1_ok(a.k_out, a.ko_idx, a.ko_val, a.ko_head_stride);
+        const bool vo_pair1 = (OUT & 2) != 0 && ko_pair1_ok(a.v_out, a.vo_idx, a.vo_val, a.vo_head_stride);
         uint32_t vo_dims = 0, vo_v01 = 0, vo_v23 = 0;
         auto vo_fetch = [&](int tile) {
             if constexpr ((OUT & 2) != 0) {
                 const int tok = t0 + tile * kTile + lane;
                 const bool ok = tile < n_tiles && tok < t1;
-                const int64_t rec = hb * a.vo_head_stride + (int64_t)(ok ? tok : t0) * a.v_out;
-                ko_load(a.vo_idx + rec, reinterpret_cast<const unsigned short*>(a.vo_val) + rec, a.v_out, vo_dims, vo_v01, vo_v23);
+                const int tk = ok ? tok : t0;
+                const int64_t rec = hb * a.vo_head_stride + (int64_t)(vo_pair1 ? (tk & ~1) : tk) * a.v_out;
+                ko_load(a.vo_idx + rec, reinterpret_cast<const unsigned short*>(a.vo_val) + rec, a.v_out, vo_pair1, vo_dims, vo_v01, vo_v23);
             }
         };
         vo_fetch(warp);
@@ -236,9 +239,10 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             if constexpr ((OUT & 1) != 0) {
                 const int tok = t0 + tile * kTile + lane;
                 const bool ok = tile < n_tiles && tok < t1;
-                const int64_t rec = hb * a.ko_head_stride + (int64_t)(ok ? tok : t0) * a.k_out;
+                const int tk = ok ? tok : t0;
+                const int64_t rec = hb * a.ko_head_stride + (int64_t)(ko_pair1 ? (tk & ~1) : tk) * a.k_out;
                 const unsigned short* vals = reinterpret_cast<const unsigned short*>(a.ko_val) + rec;
-                ko_load(a.ko_idx + rec, vals, a.k_out, ko_dims, ko_v01, ko_v23);
+                ko_load(a.ko_idx + rec, vals, a.k_out, ko_pair1, ko_dims, ko_v01, ko_v23);
             }
         };
         ko_fetch(warp);
@@ -248,10 +252,14 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             __syncwarp();
             const int tok = t0 + tile * kTile + lane;
             const bool valid = tok < t1;
-            const uint32_t my_dims = ko_dims, my_v01 = ko_v01, my_v23 = ko_v23;
+            uint32_t my_dims = ko_dims, my_v01 = ko_v01;
+            const uint32_t my_v23 = ko_v23;
             ko_fetch(tile + kWarps);
-            const uint32_t my_vdims = vo_dims, my_vv01 = vo_v01, my_vv23 = vo_v23;
+            uint32_t my_vdims = vo_dims, my_vv01 = vo_v01;
+            const uint32_t my_vv23 = vo_v23;
             vo_fetch(tile + kWarps);
+            ko_pick1(ko_pair1, lane & 1, my_dims, my_v01);       // t0 and the tile size are even: token parity = lane parity
+            ko_pick1(vo_pair1, lane & 1, my_vdims, my_vv01);
 
             // ------------------------------------------------ QK: 32 conflict-free LUT gathers for my token
             float s4[4] = {0.f, 0.f, 0.f, 0.f};

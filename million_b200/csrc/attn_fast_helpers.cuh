@@ -58,8 +58,11 @@ __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast
 // K-side outlier records of one token (k_out <= 4): dims packed one per byte, deltas two per word.  Every width is ONE load whose
 // destination IS the caller's 32-bit variable (ld.u8 / ld.u16 zero-extend into a .b32 register): a conversion or move behind the
 // load would make the warp wait for the HBM round trip on the spot instead of one tile later (measured: +20 % per launch).
-__device__ __forceinline__ void ko_load(const uint8_t* idx, const unsigned short* vals, int k_out, uint32_t& dims, uint32_t& v01, uint32_t& v23) {
-    if (k_out == 2) {
+// pair1 (k_out == 1 on an even-aligned store): the caller points at the EVEN token of the lane's pair and the two records come in
+// with the loads of the k_out == 2 case — two neighbouring lanes read the same halfword / word; ko_pick1 then selects by token
+// parity.  The single-record byte + halfword loads were 20 % slower per launch than two records per token.
+__device__ __forceinline__ void ko_load(const uint8_t* idx, const unsigned short* vals, int k_out, bool pair1, uint32_t& dims, uint32_t& v01, uint32_t& v23) {
+    if (k_out == 2 || pair1) {
         asm("ld.global.nc.u16 %0, [%1];" : "=r"(dims) : "l"(idx));
         asm("ld.global.nc.u32 %0, [%1];" : "=r"(v01) : "l"(vals));
     } else if (k_out == 4) {
@@ -73,6 +76,14 @@ __device__ __forceinline__ void ko_load(const uint8_t* idx, const unsigned short
         v01 = (uint32_t)__ldg(vals) | ((uint32_t)__ldg(vals + 1) << 16);
         v23 = __ldg(vals + 2);
     }
+}
+
+// which records of a store can be fetched as aligned pairs (kernel-uniform)
+__device__ __forceinline__ bool ko_pair1_ok(int k_out, const uint8_t* idx, const void* val, int64_t head_stride) {
+    return k_out == 1 && ((reinterpret_cast<uintptr_t>(idx) | (uintptr_t)head_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(val) & 3) == 0;
+}
+__device__ __forceinline__ void ko_pick1(bool pair1, int odd, uint32_t& dims, uint32_t& v01) {
+    if (pair1) { dims = (dims >> (8 * odd)) & 0xffu; v01 = (v01 >> (16 * odd)) & 0xffffu; }
 }
 
 }  // namespace fast

@@ -26,7 +26,16 @@ constexpr int kGrid = 64;                         // cells per axis
 constexpr int kGridCells = kGrid * kGrid;
 constexpr int kGridHdr = 32;                      // bytes: lo_x, lo_y, inv_x, inv_y, hi_x, hi_y, 0, 0
 constexpr int kGridStride = kGridHdr + kGridCells * 16;
-constexpr int kGridThreads = 512;
+#ifndef MILLION_GRID_BATCH
+#define MILLION_GRID_BATCH 3      // candidates evaluated per shared-memory round trip (A/B: 3 -> 191 us, 4 -> 196, 8 -> 198, one by one -> 199; profiles/r02_ab_variants.txt)
+#endif
+#ifndef MILLION_GRID_ILP
+#define MILLION_GRID_ILP 1
+#endif
+#ifndef MILLION_GRID_THREADS
+#define MILLION_GRID_THREADS 1024   // 32 warps per SM hide the dependent table loads better than 16 (217 -> 199 us per 8 x 32768 vectors)
+#endif
+constexpr int kGridThreads = MILLION_GRID_THREADS;
 
 int64_t encode_grid_prepared_bytes(int d, int M, int C) { return (M > 0 && d == 2 * M && C >= 2 && C <= 256 && M % 2 == 0) ? (int64_t)M * kGridStride : 0; }
 
@@ -156,6 +165,27 @@ __device__ __forceinline__ int grid_code(float px, float py, const float* __rest
         return bi;
     }
     const uint32_t w[4] = {e.x, e.y, e.z, e.w};
+#if MILLION_GRID_BATCH > 0
+    // Candidates in batches: the centroid loads and the distance arithmetic of a batch are independent of each other (ids past
+    // `cnt` are 0: a valid, ignored lookup), only the select chain is serial — one shared-memory round trip per batch instead
+    // of one per candidate (the kernel waits on exactly those: stall_short_scoreboard 33 %, stall_wait 29 %).
+#pragma unroll
+    for (int base = 0; base < 15; base += MILLION_GRID_BATCH) {
+        if (base >= cnt) break;
+        float dd[MILLION_GRID_BATCH];
+        int cc[MILLION_GRID_BATCH];
+#pragma unroll
+        for (int j = 0; j < MILLION_GRID_BATCH; ++j) {
+            const int i = base + 1 + j;
+            cc[j] = i < 16 ? (int)((w[(i >> 2) & 3] >> (8 * (i & 3))) & 0xff) : 0;
+            dd[j] = dist2_exact(px, py, cs[cc[j]]);
+        }
+#pragma unroll
+        for (int j = 0; j < MILLION_GRID_BATCH; ++j)       // ascending centroid ids: strict '<' keeps the first minimum
+            if (base + 1 + j <= cnt && dd[j] < best) { best = dd[j]; bi = cc[j]; }
+    }
+    return bi;
+#else
 #pragma unroll
     for (int i = 1; i < 16; ++i) {
         if (i > cnt) break;
@@ -164,6 +194,7 @@ __device__ __forceinline__ int grid_code(float px, float py, const float* __rest
         if (dd < best) { best = dd; bi = c; }
     }
     return bi;
+#endif
 }
 
 template <typename T>
@@ -197,6 +228,49 @@ __global__ void __launch_bounds__(kGridThreads, 1) encode_grid_kernel(const T* _
         t += kGridThreads;
         if (t >= n_tokens) { const int q = t / n_tokens; head += q; t -= q * n_tokens; }     // 32-bit, and only when a head boundary is crossed
     };
+    auto unpack = [](const Raw& r, float (&p)[4]) {
+        if constexpr (sizeof(T) == 2) {
+            const float2 a = io<T>::to_f2(r.x), b = io<T>::to_f2(r.y);
+            p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+        } else {
+            p[0] = r.x; p[1] = r.y; p[2] = r.z; p[3] = r.w;
+        }
+    };
+#if MILLION_GRID_ILP == 2
+    // two vectors per thread and iteration: four independent lookup chains (cell -> candidate ids -> centroid coordinates are
+    // dependent shared-memory loads; with 16-32 warps per SM the kernel waits on them: stall_short_scoreboard 33 %)
+    {
+        long long va = v0 + tid;
+        int ha = (int)(va / n_tokens), ta = (int)(va - (long long)ha * n_tokens);
+        int hb = ha, tb = ta;
+        advance(hb, tb);
+        Raw ra = {}, rb = {};
+        if (va < v1) ra = *row(ha, ta);
+        if (va + kGridThreads < v1) rb = *row(hb, tb);
+        while (va < v1) {
+            const long long vb = va + kGridThreads, vna = va + 2 * kGridThreads, vnb = va + 3 * kGridThreads;
+            int hna = hb, tna = tb;
+            advance(hna, tna);
+            int hnb = hna, tnb = tna;
+            advance(hnb, tnb);
+            Raw na = {}, nb = {};
+            if (vna < v1) na = *row(hna, tna);
+            if (vnb < v1) nb = *row(hnb, tnb);
+            float pa[4], pb[4];
+            unpack(ra, pa);
+            unpack(rb, pb);
+            const int a0 = grid_code(pa[0], pa[1], hdr, tab, cs, C);
+            const int b0 = grid_code(pb[0], pb[1], hdr, tab, cs, C);
+            const int a1 = grid_code(pa[2], pa[3], hdr + 8, tab + kGridCells, cs + 256, C);
+            const int b1 = grid_code(pb[2], pb[3], hdr + 8, tab + kGridCells, cs + 256, C);
+            dst.put2(ha, ta, 2 * grp, a0, a1);
+            if (vb < v1) dst.put2(hb, tb, 2 * grp, b0, b1);
+            ra = na; rb = nb;
+            va = vna; ha = hna; ta = tna; hb = hnb; tb = tnb;
+        }
+        return;
+    }
+#endif
     long long v = v0 + tid;
     int head = (int)(v / n_tokens), t = (int)(v - (long long)head * n_tokens);
     Raw raw = {};
