@@ -719,7 +719,6 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     const int Gfull = a.nh / a.nh_k;
     if (a.d != 128 || (a.M != 64 && a.M != 32) || a.C != 256 || a.code_bytes != 1) MILLION_UNSUPPORTED("fast decode attention needs d=128, M in {32, 64}, C=256, one-byte codes");
     const bool dm4 = a.M == 32;
-    if (dm4 && a.nk > 0 && a.v_layout != MILLION_V_ROWMAJOR) MILLION_UNSUPPORTED("fast decode attention, M=32: value codes must be row-major");
     if (!(Gfull == 1 || Gfull == 2 || Gfull % 4 == 0)) MILLION_UNSUPPORTED("fast decode attention needs nh/nh_k in {1,2,4k}");
     if (a.nk > 0 && a.v_layout == MILLION_V_PAGED && (a.page_size % 32 != 0 || ((uintptr_t)a.v_codes & 15)))
         MILLION_UNSUPPORTED("fast decode attention: paged V needs page_size %% 32 == 0 and an aligned pool");

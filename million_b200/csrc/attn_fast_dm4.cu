@@ -55,7 +55,8 @@ int launch_codebook_prepare_dm4(const void* kcent, const void* vcent, int io_dty
 }
 
 // One segment = the coded tokens [t0, t1) of group (b, hk) (+ this CTA's share of the window), part `split` of `np`.
-template <typename T, int G, int OUT>
+// VL = 0: value codes row-major (tokens x 32 bytes); VL = 1: transposed per sub-space ((M, ld) rows or the page pool)
+template <typename T, int G, int VL, int OUT>
 __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32_t* __restrict__ prepared, const int gsub, const int split,
                                                  const int hk, const int sub, const int b, const int t0, const int t1, const int np) {
     using namespace fast;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
         unsigned char* pbuf_w = pbuf_p + warp * kTile * 8;
         const uint32_t ks_s = smem_u32(ksp), vs_s = smem_u32(vsp);
         const uint8_t* kbase = a.k_codes + hb * a.k_head_stride;
-        const uint8_t* vbase = a.v_codes + hb * a.v_head_stride;
+        const uint8_t* vbase = a.v_codes + (a.v_layout == MILLION_V_PAGED ? 0 : hb * a.v_head_stride);
 
         uint32_t koff[8];    // byte0 = column offset for an even byte, byte1 = for an odd byte (both without the (b/2)*128 part)
 #pragma unroll
@@ -197,8 +198,39 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             }
             cp_async_commit();
         };
+        // transposed value codes: the tile is 32 sub-space rows of 32 tokens; row m is staged at row pi(m) = m/2 + 16*(m%2)
+        // (32 bytes each) so that the word reads of the PV phase below are bank-conflict free
+        auto issue_vt = [&](int tile) {
+            const int tok0 = t0 + tile * kTile;
+            const bool in_range = tile < n_tiles;
+            const uint8_t* src0 = vbase;
+            int64_t row_stride = a.v_ld;
+            if (in_range) {
+                if (a.v_layout == MILLION_V_PAGED) {
+                    const int64_t page = __ldg(a.v_page_ids + (int64_t)hb * a.n_pages + tok0 / a.page_size);
+                    src0 = a.v_codes + page * 32 * a.page_size + (tok0 % a.page_size);
+                    row_stride = a.page_size;
+                } else {
+                    src0 = vbase + tok0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int chunk = lane + i * 32;            // 0..63: 32 rows * 2 chunks of 16 tokens
+                const int m = chunk >> 1, hc = chunk & 1;
+                int ok = in_range ? (t1 - (tok0 + hc * 16)) : 0;
+                ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
+                const uint32_t dst = vs_s + (uint32_t)((((m >> 1) + 16 * (m & 1)) * 32) + hc * 16);
+                cp_async16(dst, (ok ? src0 : vbase) + (ok ? (int64_t)m * row_stride + hc * 16 : 0), ok);
+            }
+            cp_async_commit();
+        };
+        auto issue_v = [&](int tile) {
+            if constexpr (VL == 0) issue(tile, vbase, vs_s);
+            else issue_vt(tile);
+        };
         issue(warp, kbase, ks_s);
-        issue(warp, vbase, vs_s);
+        issue_v(warp);
 
         __half2 acc[2][2][G];
 #pragma unroll
@@ -356,6 +388,44 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
             __syncwarp();
 
             // ------------------------------------------------ PV: a half-warp per token, lane owns 2 sub-spaces (4 dims each)
+            if constexpr (VL == 1) {
+                // transposed codes: a word holds 4 tokens of one sub-space.  Half-warp hw takes tokens 16*hw .. 16*hw+15 in 4 groups
+                // of 4; the group order is rotated by lq/4 so the 32 word reads of one instruction hit 32 banks (staged row of
+                // sub-space 2*lq+s is lq + 16*s: bank 8*(lq%4) + 4*hw + group).
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int tgl = (u + (lq >> 2)) & 3;
+                    const int tg = tgl + 4 * hw;
+                    const uint32_t wa = lds32(vsp, lq * 32 + hw * 16 + tgl * 4);            // sub-space 2*lq
+                    const uint32_t wb = lds32(vsp, (16 + lq) * 32 + hw * 16 + tgl * 4);     // sub-space 2*lq + 1
+                    const uint32_t ws[2] = {(lq & 1) ? wb : wa, (lq & 1) ? wa : wb};        // slot sl <-> sub-space 2*lq + ((sl + lq) & 1)
+                    const uint4 pa = lds128(pbuf_w, tg * 32), pb = lds128(pbuf_w, tg * 32 + 16);
+                    const uint32_t pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __half2 p01 = as_h2(pp[2 * i]), p23 = as_h2(pp[2 * i + 1]);
+#pragma unroll
+                        for (int sl = 0; sl < 2; ++sl) {
+                            const uint32_t sel = (uint32_t)(4 + sl) | ((uint32_t)i << 4) | 0x6600u;
+                            const uint32_t ad = __byte_perm(ws[sl], voff, sel);
+                            const uint2 v = gather64<kSmemBase + kVtabOff>(ad);
+                            const __half2 v01 = as_h2(v.x), v23 = as_h2(v.y);
+                            acc[sl][0][0] = __hfma2(__low2half2(p01), v01, acc[sl][0][0]);
+                            acc[sl][1][0] = __hfma2(__low2half2(p01), v23, acc[sl][1][0]);
+                            if constexpr (G >= 2) {
+                                acc[sl][0][1] = __hfma2(__high2half2(p01), v01, acc[sl][0][1]);
+                                acc[sl][1][1] = __hfma2(__high2half2(p01), v23, acc[sl][1][1]);
+                            }
+                            if constexpr (G == 4) {
+                                acc[sl][0][2] = __hfma2(__low2half2(p23), v01, acc[sl][0][2]);
+                                acc[sl][1][2] = __hfma2(__low2half2(p23), v23, acc[sl][1][2]);
+                                acc[sl][0][3] = __hfma2(__high2half2(p23), v01, acc[sl][0][3]);
+                                acc[sl][1][3] = __hfma2(__high2half2(p23), v23, acc[sl][1][3]);
+                            }
+                        }
+                    }
+                }
+            } else
 #pragma unroll kDm4PvUnroll
             for (int jp = 0; jp < kTile / 2; ++jp) {
                 const int j = 2 * jp + hw;
@@ -382,7 +452,7 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                 }
             }
             __syncwarp();
-            issue(tile + kWarps, vbase, vs_s);
+            issue_v(tile + kWarps);
             if (++since_flush == MILLION_DM4_FLUSH_TILES) { flush(); since_flush = 0; }
         }
         flush();
@@ -503,14 +573,14 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
     if (last) merge_group<T>(a, b, hk, np, xch);
 }
 
-template <typename T, int G, int OUT>
+template <typename T, int G, int VL, int OUT>
 __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_dm4_kernel(const AttnArgs a, const uint32_t* __restrict__ prepared, const int gsub) {
     pdl_launch_dependents();
     pdl_wait();            // PDL here only hides the launch latency (attn_fast.cu also overlaps its table copies and first tiles)
     if (!a.flat) {
         int t0, t1;
         split_range(a, blockIdx.x, t0, t1);
-        attn_dm4_segment<T, G, OUT>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits);
+        attn_dm4_segment<T, G, VL, OUT>(a, prepared, gsub, blockIdx.x, blockIdx.y / gsub, blockIdx.y % gsub, blockIdx.z, t0, t1, a.n_splits);
         return;
     }
     // flat scheduling: see attn_fast_kernel (attn_fast.cu)
@@ -525,34 +595,35 @@ __global__ void __launch_bounds__(fast::kThreads, 1) attn_fast_dm4_kernel(const 
         const int first = (int)(real0 / per), last = (int)((real1 - 1) / per);
         const int us = (int)(s0 - real0), ue = (int)(s1 - real0);
         const int t1 = (ue * 64 < a.nk) ? ue * 64 : a.nk;
-        attn_dm4_segment<T, G, OUT>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1);
+        attn_dm4_segment<T, G, VL, OUT>(a, prepared, 1, (int)blockIdx.x - first, grp % a.nh_k, 0, grp / a.nh_k, us * 64, t1, last - first + 1);
         __syncthreads();
     }
 }
 
-template <typename T, int G, int OUT>
+template <typename T, int G, int VL, int OUT>
 static int launch_dm4_t(const AttnArgs& a, const uint32_t* prepared, int gsub, cudaStream_t stream) {
     using namespace fast;
     const size_t smem = dm4::kLutBytes + kVtabBytes + 32768 + 3072 + kWarps * kTile * 8 + (OUT ? 1024 : 256) + ((OUT & 2) ? kWarps * G * 128 * 4 : 0);
     static_assert(32768 + 3072 >= 2 * kWarps * 4 * 130 * sizeof(float) + 64, "stage area too small for the combine");
     static_assert(32768 + 3072 >= kMergeScratch * sizeof(float), "stage area too small for the merge scratch");
     static SmemAttrOnce configured = {};
-    MILLION_CUDA_OK(ensure_dynamic_smem(configured, attn_fast_dm4_kernel<T, G, OUT>, smem));
+    MILLION_CUDA_OK(ensure_dynamic_smem(configured, attn_fast_dm4_kernel<T, G, VL, OUT>, smem));
     dim3 grid(a.n_splits, a.nh_k * gsub, a.bs), block(kThreads);
     if (a.flat) grid = dim3((unsigned)(((long long)a.bs * a.nh_k * (a.flat_ug + kFlatPad) + a.flat_per - 1) / a.flat_per), 1, 1);
-    MILLION_CUDA_OK(launch_kernel(attn_fast_dm4_kernel<T, G, OUT>, grid, block, smem, stream, a.pdl != 0, a, prepared, gsub));
+    MILLION_CUDA_OK(launch_kernel(attn_fast_dm4_kernel<T, G, VL, OUT>, grid, block, smem, stream, a.pdl != 0, a, prepared, gsub));
     return MILLION_OK;
 }
 
 int launch_attn_fast_dm4(const AttnArgs& a, int io_dtype, int G, int gsub, const void* prepared, cudaStream_t stream) {
     const uint32_t* prep = reinterpret_cast<const uint32_t*>(prepared);
     const int kv = (a.nk > 0 && a.k_out ? 1 : 0) | (a.nk > 0 && a.v_out ? 2 : 0);     // outlier side stores: bit 0 K, bit 1 V
+    const bool vl = a.v_layout != MILLION_V_ROWMAJOR;
 #define MILLION_DM4_CASE(TT, GG)                                                  \
     switch (kv) {                                                                 \
-        case 0: return launch_dm4_t<TT, GG, 0>(a, prep, gsub, stream);            \
-        case 1: return launch_dm4_t<TT, GG, 1>(a, prep, gsub, stream);            \
-        case 2: return launch_dm4_t<TT, GG, 2>(a, prep, gsub, stream);            \
-        default: return launch_dm4_t<TT, GG, 3>(a, prep, gsub, stream);           \
+        case 0: return vl ? launch_dm4_t<TT, GG, 1, 0>(a, prep, gsub, stream) : launch_dm4_t<TT, GG, 0, 0>(a, prep, gsub, stream); \
+        case 1: return vl ? launch_dm4_t<TT, GG, 1, 1>(a, prep, gsub, stream) : launch_dm4_t<TT, GG, 0, 1>(a, prep, gsub, stream); \
+        case 2: return vl ? launch_dm4_t<TT, GG, 1, 2>(a, prep, gsub, stream) : launch_dm4_t<TT, GG, 0, 2>(a, prep, gsub, stream); \
+        default: return vl ? launch_dm4_t<TT, GG, 1, 3>(a, prep, gsub, stream) : launch_dm4_t<TT, GG, 0, 3>(a, prep, gsub, stream); \
     }
     if (io_dtype == MILLION_F16) {
         if (G == 4) MILLION_DM4_CASE(__half, 4)

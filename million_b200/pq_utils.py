@@ -604,76 +604,71 @@ class DynamicPQCache(metaclass=Singleton):
                 + sum(b.numel() * b.element_size() for b in self.registery.partial_lse_buffers.values()))
 
 
-class DecodeStepGraph:
-    """One decode step of every layer of a DynamicPQCache / PagedPQCache as a CUDA graph.
+class _GraphStep:
+    """Host side of a CUDA-graph decode step over a PQ cache: the cache POLICY of decoding() (retire a full window, count tokens,
+    start the asynchronous flush) runs on the host around a graph replay; the captured launches read the window length from a
+    device counter (million_attn_params.r_dev).  The graph is re-captured when the code stores changed (every Lt = 128 tokens,
+    64 for the paged cache): their lengths and addresses are launch parameters.  Subclasses define `_run()` = what is captured
+    (it must launch one attention call per layer through `_launch_layer` and end with `_advance()`)."""
 
-    The captured launches carry no per-token host value: the window length lives in a device counter (million_attn_params.r_dev,
-    bumped by million_counter_add at the end of the graph), each layer is ONE launch (window append fused), inputs and outputs
-    are the caller's static buffers.  The cache POLICY stays on the host and is the one of decoding() (pq_utils.py:281-327,
-    paged_pq_utils.py:341-397): before a step, full windows are retired into codes; the graph is re-captured when the code
-    stores changed (every Lt = 128 tokens, 64 for the paged cache) — their lengths and addresses are launch parameters."""
-
-    def __init__(self, cache, q, k, v, out):
-        c = cache
-        Ln = c.layer_num
-        assert q.shape == (Ln, c.bs, c.nh, 1, c.d) and out.shape == q.shape and k.shape == (Ln, c.bs, c.num_key_value_heads, 1, c.d) and v.shape == k.shape
-        for t in (q, k, v, out):
-            assert t.is_cuda and t.is_contiguous() and t.dtype == c.scalar_t
-        assert c._fused_ok(q[0], k[0], v[0]), "decode_step_graph needs nbits=8 and fp16/bf16 buffers in the cache dtype"
-        self.cache, self.q, self.k, self.v, self.out = c, q, k, v, out
-        self.r_dev = torch.zeros(1, dtype=torch.int32, device=q.device)
+    def __init__(self, cache, device, dtype):
+        self.cache, self.device, self.dtype = cache, device, dtype
+        self.r_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self._r_host = 0
         self.graph, self.sig, self.captures = None, None, 0
 
-    def _launch_all(self):
+    def _launch_layer(self, l, q, k, v, out):
+        """Append-and-attend of layer l on the current stream with the device-resident window length; q/k/v/out are tensors
+        whose addresses are baked into the capture."""
         import ctypes
         c = self.cache
-        stream = ctypes.c_void_p(torch.cuda.current_stream(self.q.device).cuda_stream)
-        sig = []
-        for l in range(c.layer_num):
-            plan = c._plan(l, self.q.dtype, self.q.device)
-            p = plan['p']
-            p.q, p.out, p.k_new, p.v_new = self.q[l].data_ptr(), self.out[l].data_ptr(), self.k[l].data_ptr(), self.v[l].data_ptr()
-            p.r, p.r_dev = 1, self.r_dev.data_ptr()
-            c._fill_stores(p, l)
-            st = plan['attn'](plan['ref'], stream)
-            if st:
-                L.check(st)
-            p.r_dev = None
-            sig.append((p.nk, p.k_codes, p.k_head_stride, p.v_codes, p.v_head_stride, p.v_page_ids, p.n_pages, p.k_out_idx, p.v_out_idx, p.k_res))
+        plan = c._plan(l, self.dtype, self.device)
+        p = plan['p']
+        p.q, p.out, p.k_new, p.v_new = q.data_ptr(), out.data_ptr(), k.data_ptr(), v.data_ptr()
+        p.r, p.r_dev = 1, self.r_dev.data_ptr()
+        c._fill_stores(p, l)
+        st = plan['attn'](plan['ref'], ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        p.r_dev = None
+        if st:
+            L.check(st)
+
+    def _advance(self):
         ops.counter_add(self.r_dev, 1)
-        return sig
 
     def _signature(self):
         c = self.cache
         sig = []
         for l in range(c.layer_num):
-            p = c._plan(l, self.q.dtype, self.q.device)['p']
+            p = c._plan(l, self.dtype, self.device)['p']
             c._fill_stores(p, l)
             sig.append((p.nk, p.k_codes, p.k_head_stride, p.v_codes, p.v_head_stride, p.v_page_ids, p.n_pages, p.k_out_idx, p.v_out_idx, p.k_res))
         return sig
 
+    def _run(self):
+        raise NotImplementedError
+
     def _capture(self, r):
-        # warm-up on the current stream (first-use attributes), then capture; both write window row r from the static buffers,
-        # which the replay writes again with the same values
+        # warm-up on the current stream (first-use attributes, library workspaces), then capture; both write window row r from
+        # the static inputs, which the replay writes again with the same values
         self.r_dev.fill_(r)
-        self._launch_all()
+        self._run()
         self.r_dev.fill_(r)
-        torch.cuda.current_stream(self.q.device).synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.sig = self._launch_all()
+            self._run()
+        self.sig = self._signature()
         self.graph = g
         self.captures += 1
         self._r_host = r
 
-    def step(self):
+    def _step(self):
         c = self.cache
         for l in range(c.layer_num):
             if c._window_full(l):
                 c._retire_window(l)
         r = c.residualed_tokens[0]
-        assert all(x == r for x in c.residualed_tokens), "decode_step_graph steps all layers together"
+        assert all(x == r for x in c.residualed_tokens), "a graph decode step advances all layers together"
         if self.graph is None or c._step_graph is not self or self._signature() != self.sig:
             c._step_graph = self
             self._capture(r)
@@ -688,4 +683,27 @@ class DecodeStepGraph:
         if c.async_flush and c._window_full(0):
             for l in range(c.layer_num):
                 c._start_async_flush(l, c._flush_len())
+
+
+class DecodeStepGraph(_GraphStep):
+    """The attention of every layer of one decode step as a CUDA graph over the caller's static buffers: each layer is ONE
+    launch (window append fused), q/out (layers, bs, nh, 1, d), k/v (layers, bs, nh_k, 1, d)."""
+
+    def __init__(self, cache, q, k, v, out):
+        c = cache
+        Ln = c.layer_num
+        assert q.shape == (Ln, c.bs, c.nh, 1, c.d) and out.shape == q.shape and k.shape == (Ln, c.bs, c.num_key_value_heads, 1, c.d) and v.shape == k.shape
+        for t in (q, k, v, out):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == c.scalar_t
+        assert c._fused_ok(q[0], k[0], v[0]), "decode_step_graph needs nbits=8 and fp16/bf16 buffers in the cache dtype"
+        super().__init__(c, q.device, q.dtype)
+        self.q, self.k, self.v, self.out = q, k, v, out
+
+    def _run(self):
+        for l in range(self.cache.layer_num):
+            self._launch_layer(l, self.q[l], self.k[l], self.v[l], self.out[l])
+        self._advance()
+
+    def step(self):
+        self._step()
         return self.out

@@ -77,3 +77,40 @@ def test_prefill_then_decode_tracks_oracle_cache():
         assert agree >= steps - 3
     assert gpu_cache.seen_tokens == ora_cache.seen_tokens == [T0 + steps] * 2
     assert gpu_cache.key_cache[0].shape[2] == T0 + 128 and gpu_cache.residualed_tokens[0] == steps - 128
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("paged", [False, True])
+def test_whole_model_graph_decoder_matches_eager_decode(paged):
+    """GraphDecoder: embeddings -> layers (projections, RoPE, PQ attention, MLP) -> LM head of one decode step replayed as ONE
+    CUDA graph; the logits must be those of the eager decode_step path, across a window flush (re-capture)."""
+    from million_b200.hf_llama import GraphDecoder, decode_step, patched_llama
+    from million_b200.paged_pq_utils import PagedPQCache
+    from million_b200.pq_utils import DynamicPQCache, Singleton
+    m16 = tiny_llama().half().cuda()
+    T0, steps = 128, 150
+    ids = torch.randint(1, 512, (1, T0 + steps), generator=torch.Generator().manual_seed(3)).cuda()
+    g = torch.Generator().manual_seed(7)
+    kc, vc = torch.randn(64, 256, 2, generator=g).half().cuda(), torch.randn(64, 256, 2, generator=g).half().cuda()
+    runs = []
+    for mode in ("eager", "graph"):
+        Singleton.clear_instance()
+        cls = PagedPQCache if paged else DynamicPQCache
+        cache = cls(bs=1, nh=8, num_key_value_heads=8, M=64, layer_num=2, d=128, scalar_t=torch.float16)
+        cache.set_cent(kc, vc)
+        out = []
+        with patched_llama(m16, cache):
+            m16(input_ids=ids[:, :T0], use_cache=False)
+            dec = GraphDecoder(m16, cache) if mode == "graph" else None
+            for s in range(steps):
+                tok = ids[:, T0 + s:T0 + s + 1]
+                lg = dec.step(tok, T0 + s) if dec else decode_step(m16, tok, T0 + s)
+                out.append(lg[:, -1].float().clone())
+        runs.append(torch.stack(out))
+        if dec:
+            assert 2 <= dec.captures <= 5
+        assert cache.seen_tokens == [T0 + steps] * 2
+    torch.cuda.synchronize()
+    # same kernels, same inputs; cuBLAS may pick different GEMM algorithms inside and outside a graph, hence a tolerance
+    assert (runs[0] - runs[1]).abs().max() < 2e-2
+    assert (runs[0].argmax(-1) == runs[1].argmax(-1)).float().mean() > 0.98

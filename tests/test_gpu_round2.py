@@ -479,3 +479,53 @@ def test_dynamic_cache_nbits10_follows_the_oracle():
     assert cache.key_cache[0].dtype == torch.uint16 and cache.key_cache[0].shape == (1, 2, 50 + 128, 64)
     assert np.array_equal(cache.key_cache[0].cpu().numpy(), oracle.key_cache[0])
     assert np.array_equal(cache.value_cache[0].cpu().numpy(), oracle.value_cache[0])
+
+
+# ------------------------------------------------------------------------------------------------ M=32: transposed / paged value codes on the fast kernel
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("v_layout", [1, 2])
+@pytest.mark.parametrize("bs,nh,nh_k,nk,r", [(1, 32, 8, 5000, 128), (2, 8, 8, 777, 17), (1, 16, 8, 64, 1), (3, 8, 2, 2100, 40)])
+def test_two_bit_fast_kernel_reads_transposed_and_paged_values(M, dtype, v_layout, bs, nh, nh_k, nk, r):
+    """M=32 ('2-bit') with the live PagedPQCache value layouts — (M, T) rows and page pool + block table — on attn_fast_dm4.cu
+    (round 1 sent these to the all-shapes kernel, > 10 ms at 32K).  IMPL_FAST: no silent fallback."""
+    from million_b200 import _lib as L
+    inp = O.make_inputs(bs=bs, nh=nh, nh_k=nh_k, nk=nk, d=128, M=32, C=256, Lt=128, seed=bs + nh + nk)
+    t = {k: dev(v) for k, v in inp.items()}
+    for k in ("q", "kcent", "vcent", "kres", "vres"):
+        t[k] = t[k].to(dtype)
+    kw = {}
+    if v_layout == 1:
+        ld = (nk + 127) // 128 * 128                      # a preallocated (M, cap) store: rows longer than nk
+        vc = torch.zeros(bs, nh_k, 32, ld, dtype=torch.uint8, device="cuda")
+        vc[..., :nk] = t["vc"].transpose(2, 3)
+    else:
+        pool, table = O.build_page_pool(inp["vc"], 64)
+        vc, kw = dev(pool), dict(v_page_ids=dev(table), page_size=64)
+    out = M.pq_decode_attn(t["q"], t["kc"], vc, t["kcent"], t["vcent"], t["kres"], t["vres"], r, nk=nk, v_layout=v_layout, impl=L.IMPL_FAST, **kw)
+    f = lambda k: t[k].float().cpu().numpy()
+    ref = O.pq_decode_attn(f("q"), inp["kc"], inp["vc"], f("kcent"), f("vcent"), f("kres"), f("vres"), r)
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=ATOL, rtol=RTOL)
+    rowmajor = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], r, impl=L.IMPL_FAST)
+    np.testing.assert_allclose(out.float().cpu().numpy(), rowmajor.float().cpu().numpy(), atol=1e-3, rtol=1e-2)
+
+
+def test_paged_cache_two_bit_runs_on_the_fast_kernel():
+    """PagedPQCache(M=32): prefill + decode across a flush against the oracle (the paged kernel name the live cache asks for)."""
+    from million_b200.paged_pq_utils import PagedPQCache
+    kw = dict(bs=1, nh=8, num_key_value_heads=2, M=32, layer_num=1, d=128)
+    kc, vc = _cents(21, 32)
+    cache = _mk(PagedPQCache, scalar_t=torch.float16, **kw)
+    cache.set_cent(dev(kc), dev(vc))
+    oracle = O.PagedPQCacheOracle(**kw)
+    oracle.set_cent(kc, vc)
+    rng = np.random.default_rng(6)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32).astype(np.float16)
+    q, k, v = f(1, 8, 192, 128), f(1, 2, 192, 128), f(1, 2, 192, 128)
+    cache.prefill(dev(q), dev(k), dev(v), 0)
+    oracle.prefill(q, k, v, 0)
+    for step in range(140):
+        q, k, v = f(1, 8, 1, 128), f(1, 2, 1, 128), f(1, 2, 1, 128)
+        out = cache.decoding_with_pages(dev(q), dev(k), dev(v), 0)
+        np.testing.assert_allclose(out.float().cpu().numpy(), oracle.decoding_with_pages(q, k, v, 0), atol=ATOL, rtol=RTOL, err_msg=f"step {step}")

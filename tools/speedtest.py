@@ -6,6 +6,7 @@ with synthetic token ids (speedtest.py:32-34), greedy decoding, through
     * baseline : HF's own attention + DynamicCache (fp16 KV), `model.generate`-style loop
     * pq       : million_b200.hf_llama.patched_llama + DynamicPQCache (4-bit PQ, window 128)
     * pq_paged : the same with PagedPQCache
+    * pq_graph : DynamicPQCache + the whole decode step (all layers, LM head) as ONE CUDA graph (hf_llama.GraphDecoder)
 
 and reports, like the reference (`time_to_first_token`, `time_per_output_token`, milliseconds), the first-token latency
 (prefill + quantisation of the whole prompt) and the mean latency of the following tokens, measured with CUDA events.
@@ -49,6 +50,25 @@ def run_baseline(model, ids, n_decode):
 
 
 @torch.no_grad()
+def run_pq_graph(model, cache, ids, n_decode):
+    """PQ cache + the whole decode step as one CUDA graph (million_b200.hf_llama.GraphDecoder)."""
+    from million_b200.hf_llama import GraphDecoder, patched_llama
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_decode + 1)]
+    T = ids.shape[1]
+    with patched_llama(model, cache):
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t0.record()
+        tok = model(input_ids=ids, use_cache=False).logits[:, -1:].argmax(-1)
+        ev[0].record()
+        dec = GraphDecoder(model, cache)
+        for i in range(n_decode):
+            tok = dec.step(tok, T + i)[:, -1:].argmax(-1)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+    return t0.elapsed_time(ev[0]), [ev[i].elapsed_time(ev[i + 1]) for i in range(n_decode)]
+
+
+@torch.no_grad()
 def run_pq(model, cache, ids, n_decode):
     from million_b200.hf_llama import decode_step, patched_llama
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_decode + 1)]
@@ -84,20 +104,20 @@ def main():
     for T in a.prefill:
         ids = torch.randint(0, cfg.vocab_size, (a.bs, T), device=dev, generator=g)
         row = {"prefill_length": T, "decoding_length": a.decode, "bs": a.bs, "layers": a.layers}
-        for name in ("baseline", "pq", "pq_paged"):
+        for name in ("baseline", "pq", "pq_paged", "pq_graph"):
             ttft, tpot = [], []
             for it in range(a.niter + 1):                # first iteration = warm-up (speedtest.py:92)
                 if name == "baseline":
                     f, d = run_baseline(model, ids, a.decode)
                 else:
                     Singleton.clear_instance()
-                    cls = DynamicPQCache if name == "pq" else PagedPQCache
+                    cls = PagedPQCache if name == "pq_paged" else DynamicPQCache
                     cache = cls(bs=a.bs, nh=32, num_key_value_heads=8, M=64, layer_num=a.layers, d=128, scalar_t=torch.float16, device=dev)
                     cache.set_cent(kcent, vcent)
-                    f, d = run_pq(model, cache, ids, a.decode)
+                    f, d = (run_pq_graph if name == "pq_graph" else run_pq)(model, cache, ids, a.decode)
                     del cache
                 if it:
-                    ttft.append(f); tpot.append(sum(d[1:]) / max(1, len(d) - 1))
+                    ttft.append(f); tpot.append(sorted(d[1:])[len(d[1:]) // 2])      # median: the graph variant's first step includes the capture
             row[name] = {"time_to_first_token": sum(ttft) / len(ttft), "time_per_output_token": sum(tpot) / len(tpot)}
         results.append(row)
         print(json.dumps(row), flush=True)
