@@ -40,7 +40,8 @@ def split_kv_ranges(nk: int, world: int, page: int = 64) -> List[Tuple[int, int]
 def split_window_rows(r: int, world: int, rank: int) -> Tuple[int, int]:
     """Rows [start, end) of the r-row fp16 window that `rank` attends over when the window is replicated on every rank (each
     rank computes the new token's k/v anyway under tensor parallelism) instead of living on the last rank only: the ranks'
-    work stays balanced, nobody waits for the one that also owns the window."""
+    work stays balanced, nobody waits for the one that also owns the window.  Every rank then appends the new token to ITS replica
+    with ops.window_append: the append fused into the attention launch (k_new / v_new) only stores a row the call attends over."""
     return r * rank // world, r * (rank + 1) // world
 
 

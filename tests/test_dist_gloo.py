@@ -25,6 +25,11 @@ def test_range_planning():
     assert list(kv) == [6, 7] and list(qh) == list(range(24, 32))
     with pytest.raises(ValueError):
         sharding.kv_head_shard(32, 8, 3, 0)
+    # the replicated window dealt out row-wise: a partition of [0, r) for every world size
+    for r, world in ((128, 8), (128, 3), (17, 4), (1, 2), (0, 4)):
+        rows = [sharding.split_window_rows(r, world, g) for g in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == r and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        assert max(e - a for a, e in rows) - min(e - a for a, e in rows) <= 1
 
 
 def _free_port():

@@ -529,3 +529,27 @@ def test_paged_cache_two_bit_runs_on_the_fast_kernel():
         q, k, v = f(1, 8, 1, 128), f(1, 2, 1, 128), f(1, 2, 1, 128)
         out = cache.decoding_with_pages(dev(q), dev(k), dev(v), 0)
         np.testing.assert_allclose(out.float().cpu().numpy(), oracle.decoding_with_pages(q, k, v, 0), atol=ATOL, rtol=RTOL, err_msg=f"step {step}")
+
+
+# ------------------------------------------------------------------------------------------------ more than one device per process
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_kernels_configure_themselves_on_every_device(M):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per device: the > 48 KB kernels (fast attention, M=32 attention, tensor-core
+    and grid encoders) must work on a second GPU of the same process (HF device_map='auto', tests iterating over devices)."""
+    from million_b200 import _lib as L
+    outs = []
+    for devi in (0, 1, 0):
+        with torch.cuda.device(devi):
+            d = torch.device("cuda", devi)
+            for Mm in (64, 32):
+                inp = O.make_inputs(bs=1, nh=8, nh_k=2, nk=2000, d=128, M=Mm, C=256, Lt=128, seed=Mm)
+                t = {k: torch.from_numpy(v).to(d) for k, v in inp.items()}
+                out = M.pq_decode_attn(t["q"], t["kc"], t["vc"], t["kcent"], t["vcent"], t["kres"], t["vres"], 33, impl=L.IMPL_FAST)
+                ref = O.pq_decode_attn(inp["q"], inp["kc"], inp["vc"], inp["kcent"], inp["vcent"], inp["kres"], inp["vres"], 33)
+                np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=ATOL, rtol=RTOL)
+                X = torch.randn(1, 2, 600, 128, device=d).half()
+                codes = M.pq_encode(X, t["kcent"].float())
+                assert np.array_equal(codes.cpu().numpy(), O.pq_encode(X.float().cpu().numpy(), inp["kcent"]))
+            torch.cuda.synchronize(d)
