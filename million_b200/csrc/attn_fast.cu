@@ -724,8 +724,7 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
         MILLION_UNSUPPORTED("fast decode attention: paged V needs page_size %% 32 == 0 and an aligned pool");
     if (a.nk > 0 && a.v_layout == MILLION_V_TRANSPOSED && ((a.v_ld & 15) || (a.v_head_stride & 15) || ((uintptr_t)a.v_codes & 15)))
         MILLION_UNSUPPORTED("fast decode attention: transposed V needs 16-byte aligned rows");
-    if (a.nk > 0 && a.v_out > 0 && ((!dm4 && Gfull > 2) || a.v_out > 4))
-        MILLION_UNSUPPORTED("fast decode attention: V-side outlier records need v_out <= 4 and, at M=64, nh/nh_k <= 2 (no shared memory left at 4 heads per CTA; the generic kernel runs the rest)");
+    if (a.nk > 0 && a.v_out > 4) MILLION_UNSUPPORTED("fast decode attention: V-side outliers need v_out <= 4");
     if (a.nk > 0 && a.v_out > 0 && a.v_out != 3 &&
         ((uintptr_t)a.vo_idx % a.v_out || a.vo_head_stride % a.v_out || (uintptr_t)a.vo_val % (2 * a.v_out)))
         MILLION_UNSUPPORTED("fast decode attention: the V-side outlier store must be aligned to one token's records");
@@ -743,7 +742,14 @@ int launch_attn_fast(const AttnArgs& a_in, int io_dtype, const void* prepared, c
     if ((a.r > 0 || a.r_dev) && (((uintptr_t)a.k_res | (uintptr_t)a.v_res | (uintptr_t)a.k_new | (uintptr_t)a.v_new) & 7))
         MILLION_UNSUPPORTED("fast decode attention needs an 8-byte aligned window");
     if (probe_only) return MILLION_OK;
-    const int G = Gfull >= 4 ? 4 : Gfull, gsub = Gfull >= 4 ? Gfull / 4 : 1;
+    int G = Gfull >= 4 ? 4 : Gfull, gsub = Gfull >= 4 ? Gfull / 4 : 1;
+    if (!dm4 && a.nk > 0 && a.v_out > 0 && G == 4) {
+        // V-side outlier records need 2 KB of shared-memory accumulators per warp, which the 4-heads-per-CTA kernel (128 KB of K
+        // LUT) does not have: such calls run as 2-head sub-groups (64 KB LUT) — the codes are streamed twice, still two orders of
+        // magnitude faster than the all-shapes kernel
+        G = 2;
+        gsub = Gfull / 2;
+    }
     if (a.auto_splits && gsub == 1 && a.nk > 0) {
         // flat scheduling pays when a CTA's share of tokens dwarfs the (up to two) prologues it runs
         int sms = sm_count();

@@ -123,12 +123,19 @@ def test_attn_fast_k_outliers_long_batch(M):
     np.testing.assert_allclose(got, ref, atol=ATOL, rtol=RTOL)
 
 
-def test_attn_auto_routes_v_outliers_to_generic(M):
+@pytest.mark.parametrize("Mm", [64, 32])
+@pytest.mark.parametrize("nh,nh_k", [(8, 8), (8, 4), (8, 2), (16, 2)])
+def test_attn_fast_v_outliers_every_group_size(M, Mm, nh, nh_k):
+    """V-side records on the fast kernels (round 2): per-warp shared-memory reduction in the QK phase.  M=32: every group size;
+    M=64: G <= 2 directly, GQA-4/8 as 2-head sub-groups.  AUTO and FAST agree with the oracle; only v_out > 4 is refused."""
     from million_b200 import _lib as L
-    got, ref = _attn_case(M, 1, 8, 2, 900, 5, 2, 2, L.IMPL_AUTO)
+    for impl in (L.IMPL_AUTO, L.IMPL_FAST):
+        got, ref = _attn_case(M, 2, nh, nh_k, 900, 5, 2, 2, impl, Mm=Mm)
+        np.testing.assert_allclose(got, ref, atol=ATOL, rtol=RTOL)
+    got, ref = _attn_case(M, 1, nh, nh_k, 700, 33, 0, 1, L.IMPL_FAST, Mm=Mm)      # a single V record: the aligned pair loads
     np.testing.assert_allclose(got, ref, atol=ATOL, rtol=RTOL)
     with pytest.raises(L.MillionError) as e:
-        _attn_case(M, 1, 8, 2, 900, 5, 2, 2, L.IMPL_FAST)
+        _attn_case(M, 1, nh, nh_k, 300, 5, 0, 5, L.IMPL_FAST, Mm=Mm)
     assert e.value.status == L.MILLION_ERR_UNSUPPORTED
 
 

@@ -553,3 +553,25 @@ def test_kernels_configure_themselves_on_every_device(M):
                 codes = M.pq_encode(X, t["kcent"].float())
                 assert np.array_equal(codes.cpu().numpy(), O.pq_encode(X.float().cpu().numpy(), inp["kcent"]))
             torch.cuda.synchronize(d)
+
+
+@pytest.mark.parametrize("nh,nh_k", [(32, 8), (16, 2)])
+def test_gqa_shapes_with_v_side_outliers_stay_on_the_fast_kernel(M, nh, nh_k):
+    """Llama-3.1-8B-style GQA with K- and V-side outlier records: the 4-heads-per-CTA kernel has no shared memory for the V
+    accumulators, so the launcher runs 2-head sub-groups — IMPL_FAST must accept it, results against the A.6 oracle."""
+    from million_b200 import _lib as L
+    bs, nk, r, d = 2, 3000, 77, 128
+    rng = np.random.default_rng(nh)
+    f16 = lambda *s: rng.standard_normal(s, dtype=np.float32).astype(np.float16)
+    kcent, vcent = f16(64, 256, 2), f16(64, 256, 2)
+    K, V = f16(bs, nh_k, nk, d), f16(bs, nh_k, nk, d)
+    K = np.where(rng.random(K.shape) < 0.01, K * 20, K).astype(np.float16)
+    V = np.where(rng.random(V.shape) < 0.01, V * 20, V).astype(np.float16)
+    q, kres, vres = f16(bs, nh, 1, d), f16(bs, nh_k, 128, d), f16(bs, nh_k, 128, d)
+    cf = lambda a: a.astype(np.float32)
+    kc_, ki, kv = M.pq_encode_outliers(dev(K), dev(cf(kcent)), 2)
+    vc_, vi, vv = M.pq_encode_outliers(dev(V), dev(cf(vcent)), 2)
+    out = M.pq_decode_attn(dev(q), kc_, vc_, dev(kcent), dev(vcent), dev(kres), dev(vres), r, k_outliers=(ki, kv), v_outliers=(vi, vv), impl=L.IMPL_FAST)
+    ref = O.pq_decode_attn_outliers(cf(q), kc_.cpu().numpy(), vc_.cpu().numpy(), cf(kcent), cf(vcent), cf(kres), cf(vres), r,
+                                    kout=(ki.cpu().numpy(), kv.float().cpu().numpy()), vout=(vi.cpu().numpy(), vv.float().cpu().numpy()))
+    _check(out, ref, f"GQA {nh}/{nh_k} outliers (2,2)")

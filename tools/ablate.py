@@ -1,4 +1,5 @@
-"""Ablation timing of attn_fast phases (temporary debug hook million_debug_set_mode)."""
+"""Ablation timing of attn_fast phases (temporary debug hook million_debug_set_mode).
+Needs a -DMILLION_DEBUG build: MILLION_NVCC_EXTRA=-DMILLION_DEBUG python -m million_b200._build --out variants/debug.so; MILLION_B200_LIB=variants/debug.so python tools/ablate.py"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,4 +1,5 @@
-"""Per-CTA phase timing of attn_fast (debug hook million_debug_set_timing_buffer): raw globaltimer stamps per piece."""
+"""Per-CTA phase timing of attn_fast (debug hook million_debug_set_timing_buffer): raw globaltimer stamps per piece.
+Needs a -DMILLION_DEBUG build: MILLION_NVCC_EXTRA=-DMILLION_DEBUG python -m million_b200._build --out variants/debug.so; MILLION_B200_LIB=$PWD/variants/debug.so python tools/attn_phases.py 8 32768"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,3 +1,4 @@
+"""Needs a -DMILLION_DEBUG build (see tools/attn_phases.py)."""
 import ctypes, os, sys
 sys.path.insert(0, "/root/repo")
 import torch
