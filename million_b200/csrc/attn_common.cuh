@@ -129,20 +129,6 @@ __host__ __device__ __forceinline__ constexpr int64_t p2p_ll_offset(int world, i
 __device__ __forceinline__ void st_tagged(float* cell, float v, unsigned tag) {
     asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(cell), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
-// spins until the cell carries `tag`; false if `limit` polls (100 ns apart) went by
-__device__ __forceinline__ bool ld_tagged(const float* cell, unsigned tag, int limit, float& v) {
-    unsigned bits, t;
-    int spins = 0;
-    for (;;) {
-        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(bits), "=r"(t) : "l"(cell) : "memory");
-        if (t == tag) break;
-        __nanosleep(100);
-        if (++spins > limit) { v = __int_as_float(0x7fc00000); return false; }
-    }
-    v = __uint_as_float(bits);
-    return true;
-}
-
 // device-memory block of the split-KV protocol (million_splitkv_state_init): read only on the merge path
 struct P2PState {
     unsigned counter; int ticket; int err; int spin_limit;   // spin_limit: polls (100 ns apart) before a wait gives up; 0 = default
@@ -347,11 +333,19 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
         for (int i = threadIdx.x; i < G * W; i += blockDim.x) {
             const int g = i / W, w = i - g * W;
             const float* p = recv + 2 * ((size_t)w * p2p_slot + (size_t)(row0 + g) * os);
-            float m, l;
-            const bool ok = ld_tagged(p + 2 * a.d, p2p_seq, limit, m) & ld_tagged(p + 2 * (a.d + 1), p2p_seq, limit, l);
+            // (m, l) are adjacent cells: one 16-byte load brings both values and both tags
+            uint4 c;
+            int spins = 0;
+            bool ok = true;
+            for (;;) {
+                asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(p + 2 * a.d) : "memory");
+                if (c.y == p2p_seq && c.w == p2p_seq) break;
+                __nanosleep(100);
+                if (++spins > limit) { ok = false; break; }
+            }
             if (!ok) { ps->err = 1; *sflag = 1; }
-            sm_m[i] = m;
-            sm_l[i] = l;
+            sm_m[i] = __uint_as_float(c.x);
+            sm_l[i] = __uint_as_float(c.z);
         }
         __syncthreads();
         for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -372,13 +366,27 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
         for (int i = threadIdx.x; i < G * a.d; i += blockDim.x) {
             const int g = i / a.d, k = i - g * a.d;
             const float* p = recv + 2 * ((size_t)(row0 + g) * os + k);
-            float acc = 0.f;
+            // all `world` cells of this output are requested at once (independent loads: one L2 round trip, not `world` of them),
+            // and polled again together until every tag is this call's
+            unsigned bits[8], tag[8];
             bool ok = !ml_timed_out;
-            for (int w = 0; w < W && ok; ++w) {
-                float v;
-                ok = ld_tagged(p + 2 * (size_t)w * p2p_slot, p2p_seq, limit, v);
-                acc = fmaf(v, sm_w[g * W + w], acc);
+            int spins = 0;
+            while (ok) {
+                bool all = true;
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    if (w < W) asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(bits[w]), "=r"(tag[w]) : "l"(p + 2 * (size_t)w * p2p_slot) : "memory");
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    if (w < W) all = all && tag[w] == p2p_seq;
+                if (all) break;
+                __nanosleep(100);
+                if (++spins > limit) ok = false;
             }
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if (w < W) acc = fmaf(__uint_as_float(bits[w]), sm_w[g * W + w], acc);
             if (!ok) ps->err = 1;
             // a wait that gave up must not pass stale rows on as a result: poison them (and P2PState.err is set)
             reinterpret_cast<T*>(a.out)[(size_t)(row0 + g) * a.d + k] = io<T>::from_f(ok ? acc : __int_as_float(0x7fc00000));
