@@ -177,6 +177,14 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
         p2p_par = p2p_seq & 1;
         p2p_rank = ps->rank; p2p_world = ps->world;
     }
+    // the peers' buffer addresses, read once: inside the store loop below every load would sit behind the previous volatile store
+    // (a chain of L2 round trips that grows with the world size)
+    unsigned char* p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if constexpr (P2P) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < p2p_world) p2p_peer[r] = ps->peer[r];
+    }
     const int slots = a.n_parts;
     const int stride = part_stride(a.d);    // workspace rows
     const int ostride = a.d + 2;            // rows of partial_out (public layout)
@@ -184,6 +192,49 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
     float* ll = scr + 2048;        // [gc][n_parts] denominators
     float* ww = scr + 4096;        // [gc][n_parts] merge weights
     float* hd = scr + 6144;        // [gc][2]: m*, den
+#ifndef MILLION_MERGE_DIRECT_PARTS
+#define MILLION_MERGE_DIRECT_PARTS 8     // A/B (us per launch at 32K, batch 8 / 4 / 2 / 1): staged merge only 97.3 / 55.9 / 32.0 / 22.5; direct up to 4 parts 93.6 / 55.8 / 32.1 / 22.5; up to 8: 94.0 / 52.2 / 32.0 / 22.4; up to 12: 94.3 / 52.6 / 31.3 / -; up to 20: 95.4 / 53.8 / 32.0 / 22.8
+#endif
+    if constexpr (!P2P) {
+        // Few parts (large batches: 2-3 CTAs per group): no staging, no barriers — every thread requests the few values of its
+        // outputs and the parts' (m, l) pairs at once (one L2 round trip) and merges them in registers.
+        if (n_parts <= MILLION_MERGE_DIRECT_PARTS) {
+            for (int i = threadIdx.x; i < G * a.d; i += blockDim.x) {
+                const int g = i / a.d, k = i - g * a.d, h = hk * G + g;
+                const float* base = a.parts + ((int64_t)(b * a.nh + h) * slots) * stride;
+                float o[MILLION_MERGE_DIRECT_PARTS > 0 ? MILLION_MERGE_DIRECT_PARTS : 1], m[MILLION_MERGE_DIRECT_PARTS > 0 ? MILLION_MERGE_DIRECT_PARTS : 1],
+                    l[MILLION_MERGE_DIRECT_PARTS > 0 ? MILLION_MERGE_DIRECT_PARTS : 1];
+#pragma unroll
+                for (int p = 0; p < MILLION_MERGE_DIRECT_PARTS; ++p) {
+                    const bool on = p < n_parts;
+                    o[p] = on ? __ldcg(base + (int64_t)p * stride + k) : 0.f;
+                    m[p] = on ? __ldcg(base + (int64_t)p * stride + a.d) : -INFINITY;
+                    l[p] = on ? __ldcg(base + (int64_t)p * stride + a.d + 1) : 0.f;
+                }
+                float mstar = -INFINITY;
+#pragma unroll
+                for (int p = 0; p < MILLION_MERGE_DIRECT_PARTS; ++p)
+                    if (l[p] > 0.f) mstar = fmaxf(mstar, m[p]);
+                float acc = 0.f, den = 0.f;
+#pragma unroll
+                for (int p = 0; p < MILLION_MERGE_DIRECT_PARTS; ++p) {
+                    const float w = l[p] > 0.f ? exp2f(m[p] - mstar) : 0.f;
+                    acc = fmaf(o[p], w, acc);
+                    den = fmaf(l[p], w, den);
+                }
+                if (a.partial_out) {
+                    a.partial_out[(int64_t)(b * a.nh + h) * ostride + k] = acc;
+                    if (k == 0) {
+                        a.partial_out[(int64_t)(b * a.nh + h) * ostride + a.d] = mstar * kLn2;   // natural-log units
+                        a.partial_out[(int64_t)(b * a.nh + h) * ostride + a.d + 1] = den;
+                    }
+                } else {
+                    reinterpret_cast<T*>(a.out)[(int64_t)(b * a.nh + h) * a.d + k] = io<T>::from_f(den > 0.f ? acc / den : 0.f);
+                }
+            }
+            return;
+        }
+    }
     int gc_max = 2048 / n_parts;
     if (gc_max < 1) gc_max = 1;    // n_parts <= 1024 is enforced by the host
     // many parts (one group spread over every SM: KV-head sharding at batch 1): take as many heads per round as the lent
@@ -296,8 +347,10 @@ __device__ __noinline__ void merge_group_impl(const MergeArgs a, int b, int hk, 
                 // buffer (NVLink stores, consecutive k = coalesced); layout of million_splitkv_push_merge
                 const size_t off = ((size_t)p2p_par * p2p_world + p2p_rank) * p2p_slot + (size_t)(b * a.nh + h) * ostride;
                 const int64_t ll_off = p2p_ll_offset(p2p_world, p2p_rows, a.d);
-                for (int r = 0; r < p2p_world; ++r) {
-                    float* dst = reinterpret_cast<float*>(ps->peer[r] + ll_off) + 2 * off;       // 8-byte cells {value, sequence tag}
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if (r >= p2p_world) break;
+                    float* dst = reinterpret_cast<float*>(p2p_peer[r] + ll_off) + 2 * off;       // 8-byte cells {value, sequence tag}
                     st_tagged(dst + 2 * k, acc, p2p_seq);
                     if (k == 0) { st_tagged(dst + 2 * a.d, hd[2 * g] * kLn2, p2p_seq); st_tagged(dst + 2 * (a.d + 1), hd[2 * g + 1], p2p_seq); }
                 }

@@ -1,4 +1,7 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -q -k "fused_splitkv or fuzz or fast_kernels" -p no:cacheprovider > gpurun_out/tests_fused.log 2>&1; tail -3 gpurun_out/tests_fused.log
-bash tools/gpu_visit_n.sh $1
+mkdir -p gpurun_out; rm -f gpurun_out/variants.log
+for rep in 1 2; do
+  for bs in 8 4 2 1; do python tools/graph_rate.py 32768 $bs 2>&1 | grep "pdl 1" >> gpurun_out/variants.log; done
+  for v in variants/direct8.so variants/direct12.so variants/direct20.so; do for bs in 8 4 2 1; do MILLION_B200_LIB=$PWD/$v python tools/graph_rate.py 32768 $bs 2>&1 | grep "pdl 1" >> gpurun_out/variants.log; done; done
+done
+sort gpurun_out/variants.log | uniq
