@@ -46,38 +46,63 @@ def measured_peaks():
 
 
 class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples DURING the timed region.  nvidia-smi needs up to a second to start (longer on an
+    8-GPU box), so the sampler is started before the warm-up (`start()` returns once the first row is in) and `window()` brackets
+    the timed region: the summary uses the rows whose host timestamps fall inside it — or, when the region is shorter than the
+    sampling period, the rows right before and after it (the GPU was under the same load during the warm-up replays)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, period_ms=50):
+        self.rows, self.proc, self.index, self.period_ms = [], None, index, period_ms
+        self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self, wait_s=4.0):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms), "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            end = time.time() + wait_s
+            while not self.rows and time.time() < end:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def __enter__(self):          # the timed region
+        if self.proc is None:
+            self.start()
+        self.t0 = time.time()
+        return self
 
     def __exit__(self, *a):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(2.5 * self.period_ms / 1e3)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
     def summary(self):
+        self.stop()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1]
+        used, where = inside, "inside the timed region"
+        if not used and self.t0 is not None:
+            before = [r for t, r in self.rows if t < self.t0][-1:]
+            after = [r for t, r in self.rows if t > self.t1][:1]
+            used, where = before + after, "adjacent to the timed region (shorter than the sampling period; same load during warm-up)"
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in used:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -86,7 +111,8 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "sampled": where,
+                "period_ms": self.period_ms}
 
 
 def workload_config(args, world):
@@ -576,10 +602,12 @@ def main():
 
     # ---- resident-inputs number (value) + roofline
     graph, layers, cents = resident_graph(torch, ops, bs_g, nh_l, nhk_l, nk, r, device, impl=args.kernel, pdl=bool(args.pdl))
+    clk = ClockSampler(local).start()                 # nvidia-smi is up before the warm-up; the GPU stays loaded from here on
     for _ in range(warmup):
         graph.replay()
-    with ClockSampler(local) as clk:
+    with clk:
         secs = T.run(graph.replay, steps)
+    clk.stop()
     launches = LAYERS * steps
     per_launch = secs / launches
     alg = algorithmic_bytes(bs_g, nk, r, nh=nh_l, nh_k=nhk_l)          # per rank = the N = 1 figure

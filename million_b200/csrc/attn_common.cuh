@@ -40,6 +40,7 @@ struct AttnArgs {
     int direct;                       // generic kernel: the M x C LUT does not fit shared memory, scores come from the centroids
     int pdl;                          // host only: launch with the programmatic-serialization attribute (MILLION_ATTN_PDL)
     int p2p;                          // host only: fused split-KV instantiation (partial_out = P2PState)
+    uint32_t zero;                    // always 0, unknown to the compiler: orders the outlier-record prefetches (attn_fast_helpers.cuh rec_take)
 #ifdef MILLION_DEBUG
     int dbg_mode;                     // ablation switch (million_debug_set_mode): bit 0 skips QK gathers, bit 1 skips PV, bit 2 tile loads
     unsigned long long* dbg_timing;   // optional (million_debug_set_timing_buffer): 64 words per CTA, see dbg_stamp

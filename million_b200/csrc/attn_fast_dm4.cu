@@ -256,20 +256,21 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
         // V-side records (OUT bit 1), same prefetch; applied in the QK phase where a lane is its token (see attn_fast.cu)
         const bool ko_pair1 = (OUT & 1) != 0 && ko_pair1_ok(a.k_out, a.ko_idx, a.ko_val, a.ko_head_stride);
         const bool vo_pair1 = (OUT & 2) != 0 && ko_pair1_ok(a.v_out, a.vo_idx, a.vo_val, a.vo_head_stride);
+        const int ko_sh = ko_pair1 ? (lane & 1) : 0, vo_sh = vo_pair1 ? (lane & 1) : 0;   // t0 and the tile size are even: token parity = lane parity
         uint32_t vo_dims = 0, vo_v01 = 0, vo_v23 = 0;
-        auto vo_fetch = [&](int tile) {
+        auto vo_fetch = [&](int tile, int dep) {
             if constexpr ((OUT & 2) != 0) {
-                const int tok = t0 + tile * kTile + lane;
+                const int tok = t0 + tile * kTile + lane + dep;
                 const bool ok = tile < n_tiles && tok < t1;
                 const int tk = ok ? tok : t0;
                 const int64_t rec = hb * a.vo_head_stride + (int64_t)(vo_pair1 ? (tk & ~1) : tk) * a.v_out;
                 ko_load(a.vo_idx + rec, reinterpret_cast<const unsigned short*>(a.vo_val) + rec, a.v_out, vo_pair1, vo_dims, vo_v01, vo_v23);
             }
         };
-        vo_fetch(warp);
-        auto ko_fetch = [&](int tile) {
+        vo_fetch(warp, 0);
+        auto ko_fetch = [&](int tile, int dep) {
             if constexpr ((OUT & 1) != 0) {
-                const int tok = t0 + tile * kTile + lane;
+                const int tok = t0 + tile * kTile + lane + dep;
                 const bool ok = tile < n_tiles && tok < t1;
                 const int tk = ok ? tok : t0;
                 const int64_t rec = hb * a.ko_head_stride + (int64_t)(ko_pair1 ? (tk & ~1) : tk) * a.k_out;
@@ -277,21 +278,28 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                 ko_load(a.ko_idx + rec, vals, a.k_out, ko_pair1, ko_dims, ko_v01, ko_v23);
             }
         };
-        ko_fetch(warp);
+        ko_fetch(warp, 0);
 
         for (int tile = warp; tile < n_tiles; tile += kWarps) {
             cp_async_wait<1>();          // pending [K(i), V(i)] -> K(i) landed
             __syncwarp();
             const int tok = t0 + tile * kTile + lane;
             const bool valid = tok < t1;
-            uint32_t my_dims = ko_dims, my_v01 = ko_v01;
-            const uint32_t my_v23 = ko_v23;
-            ko_fetch(tile + kWarps);
-            uint32_t my_vdims = vo_dims, my_vv01 = vo_v01;
-            const uint32_t my_vv23 = vo_v23;
-            vo_fetch(tile + kWarps);
-            ko_pick1(ko_pair1, lane & 1, my_dims, my_v01);       // t0 and the tile size are even: token parity = lane parity
-            ko_pick1(vo_pair1, lane & 1, my_vdims, my_vv01);
+            // the records the previous iteration's loads brought in are taken over BEFORE the next loads are issued (rec_take /
+            // rec_dep in attn_fast_helpers.cuh: the order is a data dependence, not a hope).  The parity pick of the pair loads
+            // (ko_sh / vo_sh) happens at the consumers.
+            uint32_t my_dims = 0, my_v01 = 0, my_v23 = 0, my_vdims = 0, my_vv01 = 0, my_vv23 = 0;
+            int dep = 0;
+            if constexpr ((OUT & 1) != 0) {
+                my_dims = rec_take(ko_dims, a.zero); my_v01 = rec_take(ko_v01, a.zero); my_v23 = rec_take(ko_v23, a.zero);
+                dep |= rec_dep(my_dims, my_v01, my_v23, a.zero);
+            }
+            if constexpr ((OUT & 2) != 0) {
+                my_vdims = rec_take(vo_dims, a.zero); my_vv01 = rec_take(vo_v01, a.zero); my_vv23 = rec_take(vo_v23, a.zero);
+                dep |= rec_dep(my_vdims, my_vv01, my_vv23, a.zero);
+            }
+            ko_fetch(tile + kWarps, dep);          // K and V records: both taken over before either prefetch is issued
+            vo_fetch(tile + kWarps, dep);
 
             // ------------------------------------------------ QK: 32 conflict-free LUT gathers for my token
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -314,10 +322,10 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                 for (int i = 0; i < 4; ++i)
                     if (i < a.k_out) {
                         const uint32_t pair = i < 2 ? my_v01 : my_v23;
-                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : (pair & 0xffffu));
+                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : ((pair >> (16 * ko_sh)) & 0xffffu));
                         const float dv = valid ? io<T>::to_f(*reinterpret_cast<const T*>(&hv)) : 0.f;
                         // q_g[dim] for the G heads from the [dim][head] table in shared memory (one load)
-                        const int dim = (my_dims >> (8 * i)) & 0xff;
+                        const int dim = (my_dims >> (8 * (i + ko_sh))) & 0xff;
                         const unsigned char* qrow = smem + kMiscOff + dim * (2 * G);
                         if constexpr (G == 4) {
                             const uint2 w = *reinterpret_cast<const uint2*>(qrow);
@@ -375,9 +383,9 @@ __device__ __forceinline__ void attn_dm4_segment(const AttnArgs& a, const uint32
                 for (int i = 0; i < 4; ++i)
                     if (i < a.v_out) {
                         const uint32_t pair = i < 2 ? my_vv01 : my_vv23;
-                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : (pair & 0xffffu));
+                        const unsigned short hv = (unsigned short)((i & 1) ? (pair >> 16) : ((pair >> (16 * vo_sh)) & 0xffffu));
                         const float dv = valid ? io<T>::to_f(*reinterpret_cast<const T*>(&hv)) : 0.f;
-                        const int dim = (my_vdims >> (8 * i)) & 0xff;
+                        const int dim = (my_vdims >> (8 * (i + vo_sh))) & 0xff;
 #pragma unroll
                         for (int g = 0; g < G; ++g) atomicAdd(vo_acc + g * 128 + dim, p[g] * dv);
                     }

@@ -59,18 +59,25 @@ __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast
 // destination IS the caller's 32-bit variable (ld.u8 / ld.u16 zero-extend into a .b32 register): a conversion or move behind the
 // load would make the warp wait for the HBM round trip on the spot instead of one tile later (measured: +20 % per launch).
 // pair1 (k_out == 1 on an even-aligned store): the caller points at the EVEN token of the lane's pair and the two records come in
-// with the loads of the k_out == 2 case — two neighbouring lanes read the same halfword / word; ko_pick1 then selects by token
+// with the loads of the k_out == 2 case — two neighbouring lanes read the same halfword / word; the consumers then select by token
 // parity.  The single-record byte + halfword loads were 20 % slower per launch than two records per token.
 __device__ __forceinline__ void ko_load(const uint8_t* idx, const unsigned short* vals, int k_out, bool pair1, uint32_t& dims, uint32_t& v01, uint32_t& v23) {
+    // EVERY path defines all three registers with a load.  Leaving v23 untouched where it is unused (k_out <= 2) made ptxas
+    // restore it with a register move placed after the loads; that move waits on the loads' scoreboard (shared by all of these
+    // loads), i.e. on the loads just issued — one exposed DRAM round trip per tile (M=32, 2 records: 120 -> 165 us per launch;
+    // found with tools/sass_sb_check.py).  The extra halfword load hits the sector the neighbouring load brings in.
     if (k_out == 2 || pair1) {
         asm("ld.global.nc.u16 %0, [%1];" : "=r"(dims) : "l"(idx));
         asm("ld.global.nc.u32 %0, [%1];" : "=r"(v01) : "l"(vals));
+        asm("ld.global.nc.u16 %0, [%1];" : "=r"(v23) : "l"(vals));           // unused value
     } else if (k_out == 4) {
         asm("ld.global.nc.u32 %0, [%1];" : "=r"(dims) : "l"(idx));
-        asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v01), "=r"(v23) : "l"(vals));
+        asm("ld.global.nc.u32 %0, [%1];" : "=r"(v01) : "l"(vals));
+        asm("ld.global.nc.u32 %0, [%1+4];" : "=r"(v23) : "l"(vals));
     } else if (k_out == 1) {
         asm("ld.global.nc.u8 %0, [%1];" : "=r"(dims) : "l"(idx));
         asm("ld.global.nc.u16 %0, [%1];" : "=r"(v01) : "l"(vals));
+        asm("ld.global.nc.u8 %0, [%1];" : "=r"(v23) : "l"(vals));            // unused value
     } else {   // 3 records: byte-wise (the packing below does wait for the loads: the slow but complete case)
         dims = (uint32_t)__ldg(idx) | ((uint32_t)__ldg(idx + 1) << 8) | ((uint32_t)__ldg(idx + 2) << 16);
         v01 = (uint32_t)__ldg(vals) | ((uint32_t)__ldg(vals + 1) << 16);
@@ -78,14 +85,19 @@ __device__ __forceinline__ void ko_load(const uint8_t* idx, const unsigned short
     }
 }
 
+// Hand-over of a prefetched record from the load registers to the registers the tile's consumers read, and the ordering token
+// for the NEXT prefetch.  All record loads of a warp share one hardware scoreboard, and a scoreboard wait is a wait for
+// EVERYTHING outstanding on it: whatever touches a load register after the next prefetch has been issued waits for that
+// prefetch's round trip too.  ptxas is free to sink plain copies below the next loads (it did: 120 -> 146-165 us per launch
+// on the M=32 kernel with two records per token), so the copies are XORs with a zero the compiler cannot see (z = AttnArgs::zero),
+// and the next prefetch's token index adds rec_dep() of them — a true data dependence: wait, copy, then issue.
+__device__ __forceinline__ uint32_t rec_take(uint32_t loaded, uint32_t z) { return loaded ^ z; }
+__device__ __forceinline__ int rec_dep(uint32_t a, uint32_t b, uint32_t c, uint32_t z) { return (int)((a | b | c) & z); }
+
 // which records of a store can be fetched as aligned pairs (kernel-uniform)
 __device__ __forceinline__ bool ko_pair1_ok(int k_out, const uint8_t* idx, const void* val, int64_t head_stride) {
     return k_out == 1 && ((reinterpret_cast<uintptr_t>(idx) | (uintptr_t)head_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(val) & 3) == 0;
 }
-__device__ __forceinline__ void ko_pick1(bool pair1, int odd, uint32_t& dims, uint32_t& v01) {
-    if (pair1) { dims = (dims >> (8 * odd)) & 0xffu; v01 = (v01 >> (16 * odd)) & 0xffffu; }
-}
-
 }  // namespace fast
 
 namespace fast {
