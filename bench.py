@@ -261,8 +261,16 @@ def capture(torch, fn, warm=1):
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        fn()
+    import gc
+    gc.collect()                 # a graph freed by the cyclic collector DURING a capture invalidates it (pq_utils._quiet_gc)
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(g):
+            fn()
+    finally:
+        if was:
+            gc.enable()
     return g
 
 

@@ -301,6 +301,16 @@ int million_window_append(void* k_win, void* v_win, int64_t win_head_stride,
 /* ctr[i] += delta for i < n (device int32 counters, e.g. the r_dev of million_attn_params): one tiny launch, graph capturable. */
 int million_counter_add(int32_t* ctr, int n, int delta, million_stream_t stream);
 
+/* Producer step of a decode token: rotary position embedding of the new token's query and key rows in ONE launch.
+ * Replaces transformers' apply_rotary_pos_emb as called by the reference's attention forward
+ * (scripts/modeldb/models/modeling_llama.py:500-512; ~10 elementwise launches per layer):
+ *     out = x * cos + rotate_half(x) * sin,   rotate_half(x) = cat(-x[d/2:], x[:d/2])
+ * q (bs, nh, d), k (bs, nh_k, d), cos / sin (bs, d), all contiguous, dtype = F16 | BF16 | F32; q_out / k_out may alias q / k.
+ * Each product and the sum are rounded to the dtype like the elementwise torch evaluation: results are bit-identical to it.
+ * k_out can be passed straight to million_pq_decode_attn as k_new (the window append is fused there). */
+int million_rope_qk(const void* q, const void* k, const void* cos, const void* sin, void* q_out, void* k_out,
+                    int dtype, int bs, int nh, int nh_k, int d, million_stream_t stream);
+
 /* window[:, 0:rem, :] = window[:, shift:shift+rem, :] (paged flush, paged_pq_utils.py:186-199) */
 int million_window_shift(void* k_win, void* v_win, int64_t win_head_stride, int n_heads, int shift, int rem,
                          int d, int dtype, million_stream_t stream);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "million_window_append": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, c_vp]),
     "million_counter_add": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
+    "million_rope_qk": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [ctypes.c_int] * 5 + [c_vp]),
     "million_window_shift": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, c_vp]),
 }

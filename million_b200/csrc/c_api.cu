@@ -87,6 +87,8 @@ static int g_dbg_mode = 0;
 int launch_window_append_dev(void* k_win, void* v_win, int64_t win_hs_b, const void* k_new, const void* v_new, int n_heads, int row_bytes,
                              const int* r_dev, int r_off, int res_len, cudaStream_t stream);
 int launch_counter_add(int* ctr, int n, int delta, cudaStream_t stream);
+int launch_rope_qk(const void* q, const void* k, const void* cos_, const void* sin_, void* q_out, void* k_out, int dtype, int bs, int nh,
+                   int nh_k, int d, cudaStream_t stream);
 static inline int elem_bytes(int dtype) { return dtype == MILLION_F32 ? 4 : 2; }
 
 }  // namespace million
@@ -329,6 +331,14 @@ void million_debug_set_timing_buffer(void* buf) { g_dbg_timing = reinterpret_cas
 int million_counter_add(int32_t* ctr, int n, int delta, million_stream_t stream) {
     MILLION_REQUIRE(ctr != nullptr && n >= 0, "counter_add: bad arguments");
     return launch_counter_add(ctr, n, delta, (cudaStream_t)stream);
+}
+
+int million_rope_qk(const void* q, const void* k, const void* cos_, const void* sin_, void* q_out, void* k_out, int dtype, int bs, int nh,
+                    int nh_k, int d, million_stream_t stream) {
+    MILLION_REQUIRE(q && k && cos_ && sin_ && q_out && k_out, "rope_qk: null pointer");
+    MILLION_REQUIRE(dtype >= MILLION_F16 && dtype <= MILLION_F32, "rope_qk: bad dtype");
+    MILLION_REQUIRE(bs >= 0 && nh > 0 && nh_k > 0 && d > 0 && d % 2 == 0, "rope_qk: bad shape (d must be even)");
+    return launch_rope_qk(q, k, cos_, sin_, q_out, k_out, dtype, bs, nh, nh_k, d, (cudaStream_t)stream);
 }
 
 int million_lse_merge(const float* parts, int n_parts, int64_t n_rows, int d, void* out, int io_dtype, million_stream_t stream) {

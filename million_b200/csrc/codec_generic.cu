@@ -176,4 +176,48 @@ int launch_counter_add(int* ctr, int n, int delta, cudaStream_t stream) {
     return MILLION_OK;
 }
 
+// ---------------------------------------------------------------- decode-token producer step: rotary embedding of q and k
+// out = x * cos + rotate_half(x) * sin for the ONE new token of every sequence (q_len = 1): the expression of
+// transformers' apply_rotary_pos_emb, which the reference calls in its attention forward (scripts/modeldb/models/
+// modeling_llama.py:500-512) and which costs ~10 elementwise launches per layer there.  Roundings follow the elementwise
+// evaluation in the I/O dtype (each product and the sum computed in fp32 and rounded to T), so the result is bit-identical to the
+// torch expression.  One block per (sequence, head) row, one thread per dimension pair (i, i + d/2).
+template <typename T>
+__global__ void rope_qk_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ cos_, const T* __restrict__ sin_,
+                               T* __restrict__ q_out, T* __restrict__ k_out, int nh, int nh_k, int d) {
+    const int row = blockIdx.x, heads = nh + nh_k;
+    const int b = row / heads, h = row - b * heads;
+    const T* x = h < nh ? q + ((int64_t)b * nh + h) * d : k + ((int64_t)b * nh_k + (h - nh)) * d;
+    T* y = h < nh ? q_out + ((int64_t)b * nh + h) * d : k_out + ((int64_t)b * nh_k + (h - nh)) * d;
+    const T* c = cos_ + (int64_t)b * d;
+    const T* s = sin_ + (int64_t)b * d;
+    const int half_d = d >> 1;
+    for (int i = threadIdx.x; i < half_d; i += blockDim.x) {
+        const float x1 = io<T>::to_f(x[i]), x2 = io<T>::to_f(x[i + half_d]);
+        const float a0 = io<T>::to_f(io<T>::from_f(__fmul_rn(x1, io<T>::to_f(c[i]))));
+        const float b0 = io<T>::to_f(io<T>::from_f(__fmul_rn(-x2, io<T>::to_f(s[i]))));
+        const float a1 = io<T>::to_f(io<T>::from_f(__fmul_rn(x2, io<T>::to_f(c[i + half_d]))));
+        const float b1 = io<T>::to_f(io<T>::from_f(__fmul_rn(x1, io<T>::to_f(s[i + half_d]))));
+        y[i] = io<T>::from_f(__fadd_rn(a0, b0));
+        y[i + half_d] = io<T>::from_f(__fadd_rn(a1, b1));
+    }
+}
+
+int launch_rope_qk(const void* q, const void* k, const void* cos_, const void* sin_, void* q_out, void* k_out, int dtype, int bs, int nh,
+                   int nh_k, int d, cudaStream_t stream) {
+    if (bs == 0) return MILLION_OK;
+    const int rows = bs * (nh + nh_k), threads = d / 2 <= 32 ? 32 : (d / 2 <= 64 ? 64 : 128);
+    if (dtype == MILLION_F16)
+        rope_qk_kernel<__half><<<rows, threads, 0, stream>>>((const __half*)q, (const __half*)k, (const __half*)cos_, (const __half*)sin_,
+                                                            (__half*)q_out, (__half*)k_out, nh, nh_k, d);
+    else if (dtype == MILLION_BF16)
+        rope_qk_kernel<__nv_bfloat16><<<rows, threads, 0, stream>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)cos_,
+                                                                   (const __nv_bfloat16*)sin_, (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_out, nh, nh_k, d);
+    else
+        rope_qk_kernel<float><<<rows, threads, 0, stream>>>((const float*)q, (const float*)k, (const float*)cos_, (const float*)sin_,
+                                                           (float*)q_out, (float*)k_out, nh, nh_k, d);
+    MILLION_CUDA_OK(cudaGetLastError());
+    return MILLION_OK;
+}
+
 }  // namespace million

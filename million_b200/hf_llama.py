@@ -8,7 +8,9 @@
 
 `cache` is a DynamicPQCache / PagedPQCache (or anything with the same prefill/decoding methods).  The KV state lives in
 the PQ cache, not in HF's `past_key_values` (the reference does the same and patches prepare_inputs_for_generation,
-modeling_llama.py:143-169; here `decode_step` passes explicit position ids instead).
+modeling_llama.py:143-169; here `decode_step` passes explicit position ids instead).  SURVEY 8(f)1, decode side: the rotary
+embedding of the new token's q and k is one launch of the library (`million_rope_qk`), and its k goes straight into the attention
+launch, which appends it to the window (`k_new`): per layer the producer side is projections -> 1 launch -> attention.
 """
 import contextlib
 import types
@@ -22,8 +24,17 @@ def _as_tensor(x, like):
     return torch.from_numpy(x).to(device=like.device, dtype=like.dtype)
 
 
-def make_forward(cache, distort_recent=False):
+def _rope(q, k, cos, sin, fused):
+    """apply_rotary_pos_emb of the reference's forward (modeling_llama.py:500-512).  For a decode token (q_len = 1) on the GPU the
+    library's one-launch kernel (million_rope_qk, bit-identical to the torch expression) replaces its ~10 elementwise launches."""
+    if fused and q.size(2) == 1 and q.is_cuda and q.dtype == k.dtype == cos.dtype == sin.dtype and cos.numel() == q.size(0) * q.size(3):
+        from . import ops
+        return ops.rope_qk(q, k, cos, sin)
     from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    return apply_rotary_pos_emb(q, k, cos, sin)
+
+
+def make_forward(cache, distort_recent=False, fused_rope=True):
 
     def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
         input_shape = hidden_states.shape[:-1]
@@ -32,7 +43,7 @@ def make_forward(cache, distort_recent=False):
         k = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
         v = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
         cos, sin = position_embeddings
-        q, k = apply_rotary_pos_emb(q, k, cos, sin)
+        q, k = _rope(q, k, cos, sin, fused_rope)
         if q.size(2) > 1:                                              # modeling_llama.py:540-544
             attn = cache.prefill(q.contiguous(), k.contiguous(), v.contiguous(), self.layer_idx, distort_recent)
         else:                                                          # modeling_llama.py:545-547 / 650-654
@@ -46,10 +57,10 @@ def make_forward(cache, distort_recent=False):
 
 
 @contextlib.contextmanager
-def patched_llama(model, cache, distort_recent=False):
+def patched_llama(model, cache, distort_recent=False, fused_rope=True):
     """Swap the forward of every LlamaAttention module of `model` for the PQ-cache one; restored on exit."""
     from transformers.models.llama.modeling_llama import LlamaAttention
-    fwd = make_forward(cache, distort_recent)
+    fwd = make_forward(cache, distort_recent, fused_rope)
     mods = [m for m in model.modules() if isinstance(m, LlamaAttention)]
     saved = [m.forward for m in mods]
     try:
@@ -81,7 +92,7 @@ class GraphDecoder:
             tok = dec.step(tok, T + i)[:, -1:].argmax(-1)
     """
 
-    def __init__(self, model, cache, bs=None):
+    def __init__(self, model, cache, bs=None, fused_rope=True):
         from .pq_utils import _GraphStep
         self.model, self.cache = model, cache
         dev = next(model.parameters()).device
@@ -93,7 +104,7 @@ class GraphDecoder:
 
         class _Step(_GraphStep):
             def _run(self_inner):
-                with _patched_for_graph(outer.model, self_inner):
+                with _patched_for_graph(outer.model, self_inner, fused_rope):
                     outer.logits = outer.model(input_ids=outer.tok, position_ids=outer.pos, use_cache=False).logits
                 self_inner._advance()
 
@@ -112,9 +123,9 @@ class GraphDecoder:
 
 
 @contextlib.contextmanager
-def _patched_for_graph(model, gs):
+def _patched_for_graph(model, gs, fused_rope=True):
     """Attention forward for graph capture: no host-side cache state is touched inside (that is _GraphStep's job)."""
-    from transformers.models.llama.modeling_llama import LlamaAttention, apply_rotary_pos_emb
+    from transformers.models.llama.modeling_llama import LlamaAttention
 
     def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
         input_shape = hidden_states.shape[:-1]
@@ -123,7 +134,7 @@ def _patched_for_graph(model, gs):
         k = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
         v = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
         cos, sin = position_embeddings
-        q, k = apply_rotary_pos_emb(q, k, cos, sin)
+        q, k = _rope(q, k, cos, sin, fused_rope)
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         out = torch.empty_like(q)
         gs._launch_layer(self.layer_idx, q, k, v, out)

@@ -427,6 +427,27 @@ def counter_add(ctr, delta):
     L.check(L.lib().million_counter_add(_ptr(ctr), ctr.numel(), delta, _stream(ctr)))
 
 
+def rope_qk(q, k, cos, sin, q_out=None, k_out=None):
+    """Rotary embedding of ONE new token per sequence in one launch (million_rope_qk): q (bs, nh, 1, d) or (bs, nh, d),
+    k (bs, nh_k, 1, d) or (bs, nh_k, d), cos / sin (bs, 1, d) or (bs, d) — the tensors transformers' apply_rotary_pos_emb gets
+    at q_len = 1 (reference modeling_llama.py:500-512).  Returns (q_rot, k_rot) with the shapes of q / k, bit-identical to it."""
+    _need_cuda(q)
+    d = q.shape[-1]
+    bs, nh, nh_k = q.shape[0], q.shape[1], k.shape[1]
+    if q.numel() != bs * nh * d or k.numel() != bs * nh_k * d or cos.numel() != bs * d or sin.numel() != bs * d:
+        raise ValueError("rope_qk handles one token per sequence (q_len = 1)")
+    if not (q.dtype == k.dtype == cos.dtype == sin.dtype):
+        raise ValueError("rope_qk: q, k, cos, sin must share a dtype")
+    qc, kc = q.reshape(bs, nh, d), k.reshape(bs, nh_k, d)           # views at q_len = 1 (a (bs, 1, nh, d) projection transposed)
+    qc, kc = (qc if qc.is_contiguous() else qc.contiguous()), (kc if kc.is_contiguous() else kc.contiguous())
+    cc, sc = cos.reshape(bs, d).contiguous(), sin.reshape(bs, d).contiguous()
+    q_out = torch.empty(q.shape, dtype=q.dtype, device=q.device) if q_out is None else q_out
+    k_out = torch.empty(k.shape, dtype=k.dtype, device=k.device) if k_out is None else k_out
+    assert q_out.is_contiguous() and k_out.is_contiguous() and q_out.numel() == qc.numel() and k_out.numel() == kc.numel()
+    L.check(L.lib().million_rope_qk(_ptr(qc), _ptr(kc), _ptr(cc), _ptr(sc), _ptr(q_out), _ptr(k_out), _dt(q), bs, nh, nh_k, d, _stream(q)))
+    return q_out, k_out
+
+
 def window_shift(k_win, v_win, shift, rem):
     _need_cuda(k_win, v_win)
     bs, nh, Lt, d = k_win.shape

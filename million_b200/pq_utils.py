@@ -10,6 +10,9 @@ semantics; different machinery:
 
 There is no CPU path: every compute entry point needs CUDA tensors and the built extension.
 """
+import contextlib
+import gc
+
 import torch
 
 from . import _lib as L
@@ -604,6 +607,22 @@ class DynamicPQCache(metaclass=Singleton):
                 + sum(b.numel() * b.element_size() for b in self.registery.partial_lse_buffers.values()))
 
 
+@contextlib.contextmanager
+def _quiet_gc():
+    """No cyclic garbage collection while a stream captures.  Destroying a CUDA graph (cudaGraphExecDestroy) is not permitted
+    during a capture and INVALIDATES it; a dropped decoder's graphs sit in reference cycles, so Python may free them at any
+    allocation — e.g. inside the model forward being captured (seen as a 1-in-6 `cudaErrorStreamCaptureInvalidated` when several
+    decoders were created in one process; torch 2.11's `torch.cuda.graph` no longer collects on entry).  Collect first, then hold."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
+
+
 class _GraphStep:
     """Host side of a CUDA-graph decode step over a PQ cache: the cache POLICY of decoding() (retire a full window, count tokens,
     start the asynchronous flush) runs on the host around a graph replay; the captured launches read the window length from a
@@ -655,8 +674,9 @@ class _GraphStep:
         self.r_dev.fill_(r)
         torch.cuda.current_stream(self.device).synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._run()
+        with _quiet_gc():
+            with torch.cuda.graph(g):
+                self._run()
         self.sig = self._signature()
         self.graph = g
         self.captures += 1

@@ -547,6 +547,22 @@ def make_inputs(*, bs, nh, nh_k, nk, d=128, M=64, C=256, Lt=128, seed=42, self_c
 # assigned points, an empty cluster keeps its centroid).  Parity unpinned by the reference (no vectors, RNG not reproducible).
 
 
+def rope_qk(q, k, cos, sin):
+    """Rotary position embedding of the new token's q and k (transformers' apply_rotary_pos_emb as called by the reference,
+    scripts/modeldb/models/modeling_llama.py:500-512): x * cos + rotate_half(x) * sin with rotate_half(x) = cat(-x[d/2:], x[:d/2]),
+    evaluated like torch evaluates it elementwise in the tensors' dtype: each product and the sum in fp32, rounded to the dtype.
+    q (bs, nh, d), k (bs, nh_k, d), cos / sin (bs, d); numpy float16 / float32 (bf16 callers pass float32 views of bf16 values and
+    round with their own helper)."""
+    def one(x):
+        dt = x.dtype
+        h = x.shape[-1] // 2
+        rot = np.concatenate([-x[..., h:], x[..., :h]], axis=-1)
+        a = (x.astype(np.float32) * cos[:, None, :].astype(np.float32)).astype(dt)
+        b = (rot.astype(np.float32) * sin[:, None, :].astype(np.float32)).astype(dt)
+        return (a.astype(np.float32) + b.astype(np.float32)).astype(dt)
+    return one(q), one(k)
+
+
 def kmeans_step(X, cent):
     """X (n, d) fp32, cent (M, C, dm) fp32 -> (new cent, codes (n, M), objective w.r.t. the old centroids, counts (M, C))."""
     X = _f32(X)

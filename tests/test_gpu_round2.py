@@ -575,3 +575,45 @@ def test_gqa_shapes_with_v_side_outliers_stay_on_the_fast_kernel(M, nh, nh_k):
     ref = O.pq_decode_attn_outliers(cf(q), kc_.cpu().numpy(), vc_.cpu().numpy(), cf(kcent), cf(vcent), cf(kres), cf(vres), r,
                                     kout=(ki.cpu().numpy(), kv.float().cpu().numpy()), vout=(vi.cpu().numpy(), vv.float().cpu().numpy()))
     _check(out, ref, f"GQA {nh}/{nh_k} outliers (2,2)")
+
+
+def test_graph_capture_survives_dead_graphs_in_reference_cycles():
+    """A CUDA graph destroyed by Python's cyclic collector WHILE a stream captures invalidates the capture
+    (cudaErrorStreamCaptureInvalidated; seen 1 in 6 in tools/speedtest.py, which creates several decoders per process).
+    _GraphStep._capture collects first and holds the collector during the capture."""
+    import gc
+    from million_b200.pq_utils import DynamicPQCache
+    layers, bs, nh, nh_k, d = 2, 1, 8, 2, 128
+    kc, vc = _cents(5)
+    cache = _mk(DynamicPQCache, scalar_t=torch.float16, bs=bs, nh=nh, num_key_value_heads=nh_k, M=64, layer_num=layers, d=d)
+    cache.set_cent(dev(kc), dev(vc))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for l in range(layers):
+        cache.prefill(torch.randn(bs, nh, 40, d, device="cuda", generator=g).half(), torch.randn(bs, nh_k, 40, d, device="cuda", generator=g).half(),
+                      torch.randn(bs, nh_k, 40, d, device="cuda", generator=g).half(), l)
+    dq = torch.randn(layers, bs, nh, 1, d, device="cuda", generator=g).half()
+    dk = torch.randn(layers, bs, nh_k, 1, d, device="cuda", generator=g).half()
+    dv, do = torch.randn_like(dk), torch.empty_like(dq)
+
+    class Holder:
+        pass
+    x = torch.zeros(8, device="cuda")
+    old = gc.get_threshold()
+    gc.collect()
+    gc.disable()
+    try:
+        for _ in range(3):                       # dead cycles, each holding a captured graph, not yet collected
+            h = Holder()
+            h.me, h.g = h, torch.cuda.CUDAGraph()
+            with torch.cuda.graph(h.g):
+                x.add_(1)
+            del h
+        gc.enable()
+        gc.set_threshold(1, 1, 1)                # the collector would now run at the first allocations inside the capture
+        step = cache.decode_step_graph(dq, dk, dv, do)
+        out = step.step().clone()
+    finally:
+        gc.set_threshold(*old)
+        gc.enable()
+    torch.cuda.synchronize()
+    assert step.captures == 1 and torch.isfinite(out.float()).all()
