@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MILLION_ABI_VERSION 7
+#define MILLION_ABI_VERSION 8
 
 typedef void* million_stream_t; /* cudaStream_t */
 

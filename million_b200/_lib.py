@@ -16,7 +16,7 @@ IMPL_AUTO, IMPL_GENERIC, IMPL_FAST, IMPL_GRID = 0, 1, 2, 3
 ATTN_PARTIAL_ONLY = 1
 ATTN_FUSED_SPLITKV = 2
 ATTN_PDL = 4
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
 
